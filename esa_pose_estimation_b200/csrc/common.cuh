@@ -1,0 +1,63 @@
+// Shared helpers for the sm_100a kernels of esa_pose_estimation_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/esa_pose_b200.h"
+
+namespace epb {
+
+extern thread_local int g_last_cuda_error;
+extern unsigned long long g_launch_count;
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  __atomic_fetch_add(&g_launch_count, 1ull, __ATOMIC_RELAXED);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return EPB_ERR_CUDA;
+  }
+  return EPB_OK;
+}
+
+inline int check_api(cudaError_t e) {
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return EPB_ERR_CUDA;
+  }
+  return EPB_OK;
+}
+
+#define EPB_RETURN_IF(expr)            \
+  do {                                 \
+    int _s = (expr);                   \
+    if (_s != EPB_OK) return _s;       \
+  } while (0)
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+  return __shfl_xor_sync(FULL, v, m);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+  return v;
+}
+__device__ __forceinline__ double bcast_d(double v, int lane) { return __shfl_sync(FULL, v, lane); }
+
+// streaming 128-bit load that does not allocate in L1 (data is touched once)
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+}  // namespace epb

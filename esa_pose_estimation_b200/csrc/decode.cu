@@ -1,0 +1,177 @@
+// Heatmap decoding for sm_100a: arg-max + log-domain sub-pixel refinement in one pass.
+//
+// Replaces (paths under /root/reference): val.py:151-164 (two-stage torch.max + 150 .item()
+// syncs + full D2H per frame), inference.py:22-51 get_max_preds, :75-94 my_taylor,
+// :136-152 get_final, :171-186 getPrediction.
+//
+// HBM-bound: every heatmap byte is read exactly once with 128-bit streaming loads
+// (ld.global.nc.L1::no_allocate), 4 independent loads in flight per thread; the 9 samples of
+// the sub-pixel stencil are re-read from L2.  Algorithmic traffic 4*H*W B per map in,
+// 16 B per map out.  Small maps (<= 64x64) use one warp per keypoint map, larger maps one
+// 256-thread CTA per map so that a single frame still spreads over many SMs.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace epb {
+
+// torch.max / np.argmax semantics: NaN is the maximum; first occurrence wins.
+__device__ __forceinline__ bool gt_nanmax(float v, float bv) {
+  return v > bv || (v != v && bv == bv);
+}
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+  if (gt_nanmax(v, bv)) return true;
+  if (gt_nanmax(bv, v)) return false;
+  return i < bi;  // equal (or both NaN): lower flat index
+}
+
+// inference.py:75-94 my_taylor on the clipped map (inference.py:141): returns true and the
+// refined coordinate when the step is applied.  math.log of Python floats = FP64.
+__device__ __forceinline__ bool subpixel_offset(const float* __restrict__ p, int H, int W, int px, int py,
+                                                double& off_x, double& off_y) {
+  if (!(px > 1 && px < W - 2 && py > 1 && py < H - 2)) return false;
+  const float clipv = 1e-10f;  // np.maximum(hm_f32, 1e-10) stays float32
+  auto lg = [&](int yy, int xx) { return log((double)fmaxf(__ldg(p + (size_t)yy * W + xx), clipv)); };
+  const double c = lg(py, px);
+  const double hx = 0.5 * (lg(py, px + 1) - lg(py, px - 1));
+  const double hy = 0.5 * (lg(py + 1, px) - lg(py - 1, px));
+  const double hxx = 0.25 * (lg(py, px + 2) - 2 * c + lg(py, px - 2));
+  const double hyy = 0.25 * (lg(py + 2, px) - 2 * c + lg(py - 2, px));
+  if (hxx != 0 && hyy != 0) {
+    const double ox = -hx / hxx, oy = -hy / hyy;
+    if (ox < 1 && oy < 1) {             // no lower bound, inference.py:92
+      off_x = ox; off_y = oy;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int THREADS, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+decode_kernel(const float* __restrict__ hm, int n_maps, int H, int W, int flags,
+              float* __restrict__ xy, float* __restrict__ maxval, int32_t* __restrict__ idx_out) {
+  constexpr int MAPS_PER_BLOCK = BLOCK / THREADS;
+  constexpr int WARPS_PER_MAP = THREADS / 32;
+  const int local_map = threadIdx.x / THREADS;
+  const int t = threadIdx.x % THREADS;
+  const int map = blockIdx.x * MAPS_PER_BLOCK + local_map;
+  const bool live = map < n_maps;
+  const int n = H * W;
+  const float* p = hm + (size_t)(live ? map : 0) * n;
+
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  if (live) {
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      const int n4 = n >> 2;
+      int i = t;
+      for (; i + 3 * THREADS < n4; i += 4 * THREADS) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream_f4(p4 + i + u * THREADS);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = (i + u * THREADS) << 2;
+          if (gt_nanmax(v[u].x, bv)) { bv = v[u].x; bi = e; }
+          if (gt_nanmax(v[u].y, bv)) { bv = v[u].y; bi = e + 1; }
+          if (gt_nanmax(v[u].z, bv)) { bv = v[u].z; bi = e + 2; }
+          if (gt_nanmax(v[u].w, bv)) { bv = v[u].w; bi = e + 3; }
+        }
+      }
+      for (; i < n4; i += THREADS) {
+        const float4 v = ldg_stream_f4(p4 + i);
+        const int e = i << 2;
+        if (gt_nanmax(v.x, bv)) { bv = v.x; bi = e; }
+        if (gt_nanmax(v.y, bv)) { bv = v.y; bi = e + 1; }
+        if (gt_nanmax(v.z, bv)) { bv = v.z; bi = e + 2; }
+        if (gt_nanmax(v.w, bv)) { bv = v.w; bi = e + 3; }
+      }
+    } else {
+      for (int i = t; i < n; i += THREADS) {
+        const float v = __ldg(p + i);
+        if (gt_nanmax(v, bv)) { bv = v; bi = i; }
+      }
+    }
+  }
+  // warp reduce (value, first index)
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const float ov = __shfl_xor_sync(FULL, bv, m);
+    const int oi = __shfl_xor_sync(FULL, bi, m);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (WARPS_PER_MAP > 1) {
+    __shared__ float sv[BLOCK / 32];
+    __shared__ int si[BLOCK / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (t < 32) {
+      const int w0 = local_map * WARPS_PER_MAP;
+      bv = (lane < WARPS_PER_MAP) ? sv[w0 + lane] : -INFINITY;
+      bi = (lane < WARPS_PER_MAP) ? si[w0 + lane] : 0x7fffffff;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const float ov = __shfl_xor_sync(FULL, bv, m);
+        const int oi = __shfl_xor_sync(FULL, bi, m);
+        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+      }
+    }
+  }
+  if (!live || t != 0) return;
+  if (bi == 0x7fffffff) bi = 0;  // all -inf: np.argmax returns 0
+  const int px = bi % W, py = bi / W;
+  float fx = (float)px, fy = (float)py;
+  double ox, oy;
+  if ((flags & EPB_DECODE_REFINE) && subpixel_offset(p, H, W, px, py, ox, oy)) {
+    fx = (float)((double)px + ox);  // numpy: float32 array += float64 list -> one rounding
+    fy = (float)((double)py + oy);
+  }
+  if ((flags & EPB_DECODE_ZERO_NONPOS) && !(bv > 0.0f)) { fx = 0.f; fy = 0.f; }
+  if (xy) { xy[2 * map] = fx; xy[2 * map + 1] = fy; }
+  if (maxval) maxval[map] = bv;
+  if (idx_out) idx_out[map] = bi;
+}
+
+// inference.py:136-152 get_final on caller-supplied integer peaks: coords [n_maps,2] in/out.
+__global__ void refine_keypoints_kernel(const float* __restrict__ hm, int n_maps, int H, int W,
+                                        float* __restrict__ xy) {
+  const int map = blockIdx.x * blockDim.x + threadIdx.x;
+  if (map >= n_maps) return;
+  float fx = xy[2 * map], fy = xy[2 * map + 1];
+  const int px = (int)fx, py = (int)fy;  // int(coord[0]) truncation, inference.py:79-80
+  double ox, oy;
+  if (subpixel_offset(hm + (size_t)map * H * W, H, W, px, py, ox, oy)) {
+    xy[2 * map] = (float)((double)fx + ox);  // coord += offset on the float32 coordinate
+    xy[2 * map + 1] = (float)((double)fy + oy);
+  }
+}
+
+}  // namespace epb
+
+extern "C" int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, int flags, float* xy,
+                                   float* maxval, int32_t* idx, void* stream) {
+  using namespace epb;
+  if (!hm || n_maps < 0 || H <= 0 || W <= 0 || (long long)H * W > 0x7fffffffLL) return EPB_ERR_INVALID;
+  if (n_maps == 0) return EPB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (H * W <= 64 * 64) {
+    constexpr int BLOCK = 128;
+    decode_kernel<32, BLOCK><<<(n_maps + 3) / 4, BLOCK, 0, s>>>(hm, n_maps, H, W, flags, xy, maxval, idx);
+  } else {
+    constexpr int BLOCK = 256;
+    decode_kernel<256, BLOCK><<<n_maps, BLOCK, 0, s>>>(hm, n_maps, H, W, flags, xy, maxval, idx);
+  }
+  return check_launch();
+}
+
+extern "C" int epb_refine_keypoints(const float* hm, int n_maps, int H, int W, float* xy, void* stream) {
+  using namespace epb;
+  if (!hm || !xy || n_maps < 0 || H <= 0 || W <= 0) return EPB_ERR_INVALID;
+  if (n_maps == 0) return EPB_OK;
+  refine_keypoints_kernel<<<(n_maps + 127) / 128, 128, 0, (cudaStream_t)stream>>>(hm, n_maps, H, W, xy);
+  return check_launch();
+}

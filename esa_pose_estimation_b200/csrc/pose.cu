@@ -1,0 +1,998 @@
+// Per-image pose solve for sm_100a: EPnP-RANSAC initialisation + Levenberg-Marquardt refinement,
+// one warp per image, one lane per 2-D/3-D correspondence (n <= 32), FP64 throughout.
+//
+// Replaces (paths under /root/reference):
+//   pnp.py:46-90           pnp(): cv2.solvePnPRansac(flags=EPNP, reprojectionError=5) + Rodrigues
+//   val.py:197-207         Rodrigues round trips, cpnp.cpnp_m (Ceres LM; binary/source absent)
+//   lib/utils/extend_utils/src/uncertainty_pnp.cpp:7-92   the cost + ceres::Solve the LM follows
+//   lib/utils/extend_utils/include/ceres/tiny_solver.h:150-293  the LM recipe
+//   val.py:172-193,203-228 keypoint selection, un-crop, quaternion packaging
+//   demo.py:295-310        ESA score
+// The EPnP statement (control points with OpenCV's SVD sign convention, RANSAC driven by
+// cv::RNG(-1) samples of 5, float32-rounded inputs) is the one validated on the CPU in
+// oracle/epnp_port.py; this file transliterates it.
+//
+// Latency/FP64-bound, ~360 B of traffic per pose: no tiling to speak of; the design goal is
+// to keep thousands of independent warps resident (4 warps/CTA, ~7 KB smem per CTA).
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace epb {
+
+constexpr int POSE_WARPS = 4;
+
+struct WarpScratch {
+  double A[12][12];  // M^T M, destroyed by the eigen-solver
+  double V[12][12];  // eigenvectors (columns)
+  double S[40];      // reduced sums / scratch
+  double L[6][10];
+  double vs[4][12];  // the four null-space vectors, ascending eigenvalue
+  int order[12];
+};
+
+struct Cam { double fu, fv, uc, vc; };
+
+// ------------------------------------------------------------------------------ small linear algebra
+// OpenCV cv::SVD (JacobiSVDImpl_) on a 3x3: rows of `at` are the columns of A.  Sign convention
+// matters for the EPnP control points (oracle/epnp_port.py svd_onesided_cv).
+__device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[9]) {
+  double at[3][3], v[3][3], ww[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { at[i][j] = a[j * 3 + i]; v[i][j] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ww[i] = at[i][0] * at[i][0] + at[i][1] * at[i][1] + at[i][2] * at[i][2];
+  const double eps = DBL_EPSILON * 10;
+  for (int it = 0; it < 30; ++it) {
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j) {
+        const double aa = ww[i], bb = ww[j];
+        double p = at[i][0] * at[j][0] + at[i][1] * at[j][1] + at[i][2] * at[j][2];
+        if (!(fabs(p) <= eps * sqrt(aa * bb))) {
+          p *= 2.0;
+          const double beta = aa - bb, gamma = hypot(p, beta);
+          double c, s;
+          if (beta < 0) {
+            const double delta = (gamma - beta) * 0.5;
+            s = sqrt(delta / gamma);
+            c = p / (gamma * s * 2.0);
+          } else {
+            c = sqrt((gamma + beta) / (gamma * 2.0));
+            s = p / (gamma * c * 2.0);
+          }
+          double na = 0, nb = 0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double t0 = c * at[i][k] + s * at[j][k], t1 = -s * at[i][k] + c * at[j][k];
+            at[i][k] = t0; at[j][k] = t1; na += t0 * t0; nb += t1 * t1;
+            const double u0 = c * v[i][k] + s * v[j][k], u1 = -s * v[i][k] + c * v[j][k];
+            v[i][k] = u0; v[j][k] = u1;
+          }
+          ww[i] = na; ww[j] = nb;
+          changed = true;
+        }
+      }
+    if (!changed) break;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) ww[i] = sqrt(at[i][0] * at[i][0] + at[i][1] * at[i][1] + at[i][2] * at[i][2]);
+  auto swap_rows = [&](int i, int j) {
+    double t = ww[i]; ww[i] = ww[j]; ww[j] = t;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      t = at[i][k]; at[i][k] = at[j][k]; at[j][k] = t;
+      t = v[i][k]; v[i][k] = v[j][k]; v[j][k] = t;
+    }
+  };
+  // selection sort, descending, first maximum (OpenCV: if (W[j] < W[k]) j = k)
+  {
+    const bool j1 = ww[0] < ww[1];
+    const double m01 = j1 ? ww[1] : ww[0];
+    const bool j2 = m01 < ww[2];
+    if (j2) swap_rows(0, 2); else if (j1) swap_rows(0, 1);
+    if (ww[1] < ww[2]) swap_rows(1, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    w[i] = ww[i];
+    const double inv = ww[i] > 0 ? 1.0 / ww[i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ut[i * 3 + k] = at[i][k] * inv; vt[i * 3 + k] = v[i][k]; }
+  }
+}
+
+// Cyclic Jacobi eigen-decomposition of the symmetric 12x12 in shared memory; lanes 0..11 apply
+// each rotation to one row/column element.  Eigenvectors end up in the columns of V.
+__device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
+  for (int e = lane; e < 144; e += 32) ws.V[e / 12][e % 12] = (e / 12 == e % 12) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0, diag = 0;
+    for (int e = lane; e < 144; e += 32) {
+      const int r = e / 12, c = e % 12;
+      const double x = ws.A[r][c];
+      if (r < c) off += x * x; else if (r == c) diag += x * x;
+    }
+    off = warp_sum(off);
+    double dmin = INFINITY;
+    for (int i = 0; i < 12; ++i) dmin = fmin(dmin, fabs(ws.A[i][i]));
+    // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the
+    // null-space vectors are what EPnP needs); exact null spaces fall through to the absolute test
+    if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
+    (void)diag;
+    for (int p = 0; p < 11; ++p)
+      for (int q = p + 1; q < 12; ++q) {
+        const double apq = ws.A[p][q];
+        if (apq != 0.0) {   // warp-uniform
+          const double app = ws.A[p][p], aqq = ws.A[q][q];
+          const double theta = (aqq - app) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+          __syncwarp();
+          if (lane < 12) {
+            const int k = lane;
+            if (k != p && k != q) {
+              const double akp = ws.A[k][p], akq = ws.A[k][q];
+              const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
+              ws.A[k][p] = np_; ws.A[p][k] = np_; ws.A[k][q] = nq_; ws.A[q][k] = nq_;
+            }
+            const double vkp = ws.V[k][p], vkq = ws.V[k][q];
+            ws.V[k][p] = c * vkp - s * vkq; ws.V[k][q] = s * vkp + c * vkq;
+          } else if (lane == 12) {
+            ws.A[p][p] = app - t * apq; ws.A[q][q] = aqq + t * apq; ws.A[p][q] = 0.0; ws.A[q][p] = 0.0;
+          }
+          __syncwarp();
+        }
+      }
+  }
+  __syncwarp();
+  // ascending order of the eigenvalues (stable), computed redundantly
+  if (lane == 0) {
+    for (int i = 0; i < 12; ++i) ws.order[i] = i;
+    for (int i = 1; i < 12; ++i) {
+      const int oi = ws.order[i];
+      const double wi = ws.A[oi][oi];
+      int j = i - 1;
+      while (j >= 0 && ws.A[ws.order[j]][ws.order[j]] > wi) { ws.order[j + 1] = ws.order[j]; --j; }
+      ws.order[j + 1] = oi;
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < 48; e += 32) ws.vs[e / 12][e % 12] = ws.V[e % 12][ws.order[e / 12]];
+  __syncwarp();
+}
+
+// Householder least squares, 6 x N (N <= 5), fully unrolled so everything stays in registers.
+template <int N>
+__device__ void lstsq6(double (&a)[6][N], double (&b)[6], double (&x)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    double nrm = 0;
+#pragma unroll
+    for (int i = k; i < 6; ++i) nrm += a[i][k] * a[i][k];
+    double alpha = sqrt(nrm);
+    if (alpha != 0.0) {
+      if (a[k][k] > 0) alpha = -alpha;
+      double vk[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) vk[i] = (i >= k) ? a[i][k] : 0.0;
+      vk[k] -= alpha;
+      double vn2 = 0;
+#pragma unroll
+      for (int i = k; i < 6; ++i) vn2 += vk[i] * vk[i];
+      if (vn2 != 0.0) {
+        const double inv = 2.0 / vn2;
+#pragma unroll
+        for (int j = k; j < N; ++j) {
+          double d = 0;
+#pragma unroll
+          for (int i = k; i < 6; ++i) d += vk[i] * a[i][j];
+          d *= inv;
+#pragma unroll
+          for (int i = k; i < 6; ++i) a[i][j] -= d * vk[i];
+        }
+        double d = 0;
+#pragma unroll
+        for (int i = k; i < 6; ++i) d += vk[i] * b[i];
+        d *= inv;
+#pragma unroll
+        for (int i = k; i < 6; ++i) b[i] -= d * vk[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    double s = b[i];
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) s -= a[i][j] * x[j];
+    x[i] = s / a[i][i];
+  }
+}
+
+// ------------------------------------------------------------------------------ EPnP
+struct PoseRT { double R[9]; double t[3]; double err; };
+
+__device__ void compute_r_and_t(const WarpScratch& ws, const double be[4], const double al[4],
+                                const double pw[3], double u, double v, bool active, int n,
+                                int first_lane, const double pw0[3], const Cam& cam, PoseRT& out) {
+  double ccs[4][3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      ccs[j][k] = be[0] * ws.vs[0][3 * j + k] + be[1] * ws.vs[1][3 * j + k] +
+                  be[2] * ws.vs[2][3 * j + k] + be[3] * ws.vs[3][3 * j + k];
+  double pc[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    pc[k] = al[0] * ccs[0][k] + al[1] * ccs[1][k] + al[2] * ccs[2][k] + al[3] * ccs[3][k];
+  const double z0 = __shfl_sync(FULL, pc[2], first_lane);
+  if (z0 < 0.0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pc[k] = -pc[k];
+  }
+  double pc0[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) pc0[k] = warp_sum(active ? pc[k] : 0.0) / n;
+  double abt[9];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      abt[3 * j + k] = warp_sum(active ? (pc[j] - pc0[j]) * (pw[k] - pw0[k]) : 0.0);
+  double w[3], ut[9], vt[9];
+  svd3_cv(abt, w, ut, vt);
+  double* R = out.R;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      R[3 * i + j] = ut[0 * 3 + i] * vt[0 * 3 + j] + ut[1 * 3 + i] * vt[1 * 3 + j] + ut[2 * 3 + i] * vt[2 * 3 + j];
+  const double det = R[0] * R[4] * R[8] + R[1] * R[5] * R[6] + R[2] * R[3] * R[7] -
+                     R[2] * R[4] * R[6] - R[1] * R[3] * R[8] - R[0] * R[5] * R[7];
+  if (det < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) out.t[i] = pc0[i] - (R[3 * i] * pw0[0] + R[3 * i + 1] * pw0[1] + R[3 * i + 2] * pw0[2]);
+  const double xc = R[0] * pw[0] + R[1] * pw[1] + R[2] * pw[2] + out.t[0];
+  const double yc = R[3] * pw[0] + R[4] * pw[1] + R[5] * pw[2] + out.t[1];
+  const double inv_z = 1.0 / (R[6] * pw[0] + R[7] * pw[1] + R[8] * pw[2] + out.t[2]);
+  const double du = u - (cam.uc + cam.fu * xc * inv_z), dv = v - (cam.vc + cam.fv * yc * inv_z);
+  out.err = warp_sum(active ? sqrt(du * du + dv * dv) : 0.0) / n;
+}
+
+// EPnP over the lanes flagged `active` (n = popcount >= 4).  All lanes return the same pose.
+__device__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int first_lane,
+                          const double pw_in[3], double u, double v, const Cam& cam, PoseRT& best) {
+  double pw[3] = {active ? pw_in[0] : 0.0, active ? pw_in[1] : 0.0, active ? pw_in[2] : 0.0};
+  // control points: centroid + PCA axes (OpenCV SVD sign convention)
+  double c0[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c0[k] = warp_sum(pw[k]) / n;
+  double d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d[k] = active ? pw[k] - c0[k] : 0.0;
+  double cov[9];
+  cov[0] = warp_sum(d[0] * d[0]); cov[1] = warp_sum(d[0] * d[1]); cov[2] = warp_sum(d[0] * d[2]);
+  cov[4] = warp_sum(d[1] * d[1]); cov[5] = warp_sum(d[1] * d[2]); cov[8] = warp_sum(d[2] * d[2]);
+  cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
+  double w[3], uct[9], vt_unused[9];
+  svd3_cv(cov, w, uct, vt_unused);
+  double kk[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) kk[i] = sqrt(w[i] / n);
+  // barycentric coordinates: CC = [k_i * uct_i] has orthogonal columns, CC^-1 rows = uct_i / k_i
+  double al[4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double inv = kk[i] > 1e-12 * kk[0] ? 1.0 / kk[i] : 0.0;
+    al[i + 1] = (uct[3 * i] * d[0] + uct[3 * i + 1] * d[1] + uct[3 * i + 2] * d[2]) * inv;
+  }
+  al[0] = 1.0 - al[1] - al[2] - al[3];
+  if (!active) { al[0] = al[1] = al[2] = al[3] = 0.0; }
+  // M^T M from four families of pair sums
+  const double du = cam.uc - u, dv = cam.vc - v, q = du * du + dv * dv;
+  {
+    int e = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = j; k < 4; ++k) {
+        const double aa = al[j] * al[k];
+        const double s0 = warp_sum(aa), s1 = warp_sum(aa * du), s2 = warp_sum(aa * dv), s3 = warp_sum(aa * q);
+        if (lane == 0) { ws.S[e] = s0; ws.S[10 + e] = s1; ws.S[20 + e] = s2; ws.S[30 + e] = s3; }
+        ++e;
+      }
+  }
+  __syncwarp();
+  for (int e = lane; e < 144; e += 32) {
+    const int r = e / 12, c = e % 12;
+    const int j = r / 3, cr = r % 3, k = c / 3, cc = c % 3;
+    const int lo = j < k ? j : k, hi = j < k ? k : j;
+    const int pidx = lo * 4 - lo * (lo - 1) / 2 + (hi - lo);  // index of pair (lo,hi), lo<=hi
+    const double s0 = ws.S[pidx], s1 = ws.S[10 + pidx], s2 = ws.S[20 + pidx], s3 = ws.S[30 + pidx];
+    double val;
+    if (cr == 0 && cc == 0) val = s0 * cam.fu * cam.fu;
+    else if (cr == 1 && cc == 1) val = s0 * cam.fv * cam.fv;
+    else if (cr == 2 && cc == 2) val = s3;
+    else if ((cr == 0 && cc == 2) || (cr == 2 && cc == 0)) val = s1 * cam.fu;
+    else if ((cr == 1 && cc == 2) || (cr == 2 && cc == 1)) val = s2 * cam.fv;
+    else val = 0.0;
+    ws.A[r][c] = val;
+  }
+  __syncwarp();
+  jacobi_eigh12(ws, lane);
+  // L_6x10 and rho
+  {
+    const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+    for (int e = lane; e < 60; e += 32) {
+      const int i = e / 10, c = e % 10;
+      // column c <-> (m,n): B11 B12 B22 B13 B23 B33 B14 B24 B34 B44
+      const int cm[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3}, cn[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
+      const int m = cm[c], nn = cn[c];
+      double dot = 0;
+      for (int k = 0; k < 3; ++k) {
+        const double dm = ws.vs[m][3 * pa[i] + k] - ws.vs[m][3 * pb[i] + k];
+        const double dn = ws.vs[nn][3 * pa[i] + k] - ws.vs[nn][3 * pb[i] + k];
+        dot += dm * dn;
+      }
+      ws.L[i][c] = (m == nn) ? dot : 2.0 * dot;
+    }
+  }
+  __syncwarp();
+  // rho: squared distances between control points = k_i^2 (+ k_j^2), since the axes are orthonormal;
+  // computed from the control points themselves like the reference implementation
+  double cw[4][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    cw[0][k] = c0[k];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cw[i + 1][k] = c0[k] + kk[i] * uct[3 * i + k];
+  }
+  double rho[6];
+  {
+    auto d2 = [&](int a, int b) {
+      const double x = cw[a][0] - cw[b][0], y = cw[a][1] - cw[b][1], z = cw[a][2] - cw[b][2];
+      return x * x + y * y + z * z;
+    };
+    rho[0] = d2(0, 1); rho[1] = d2(0, 2); rho[2] = d2(0, 3); rho[3] = d2(1, 2); rho[4] = d2(1, 3); rho[5] = d2(2, 3);
+  }
+  double pw0[3] = {c0[0], c0[1], c0[2]};
+
+  best.err = INFINITY;
+#pragma unroll 1
+  for (int cand = 0; cand < 3; ++cand) {
+    double be[4] = {0, 0, 0, 0};
+    if (cand == 0) {          // [B11 B12 B13 B14]
+      double a[6][4], b[6], x[4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][3]; a[i][3] = ws.L[i][6]; b[i] = rho[i]; }
+      lstsq6<4>(a, b, x);
+      if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = -x[1] / be[0]; be[2] = -x[2] / be[0]; be[3] = -x[3] / be[0]; }
+      else { be[0] = sqrt(x[0]); be[1] = x[1] / be[0]; be[2] = x[2] / be[0]; be[3] = x[3] / be[0]; }
+    } else if (cand == 1) {   // [B11 B12 B22]
+      double a[6][3], b[6], x[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][2]; b[i] = rho[i]; }
+      lstsq6<3>(a, b, x);
+      if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+      else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+      if (x[1] < 0) be[0] = -be[0];
+    } else {                  // [B11 B12 B22 B13 B23]
+      double a[6][5], b[6], x[5];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][2]; a[i][3] = ws.L[i][3]; a[i][4] = ws.L[i][4];
+        b[i] = rho[i];
+      }
+      lstsq6<5>(a, b, x);
+      if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+      else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+      if (x[1] < 0) be[0] = -be[0];
+      be[2] = x[3] / be[0];
+    }
+    // 5 Gauss-Newton steps on the control-point distance constraints
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) {
+      double a[6][4], b[6], x[4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double* r = ws.L[i];
+        a[i][0] = 2 * r[0] * be[0] + r[1] * be[1] + r[3] * be[2] + r[6] * be[3];
+        a[i][1] = r[1] * be[0] + 2 * r[2] * be[1] + r[4] * be[2] + r[7] * be[3];
+        a[i][2] = r[3] * be[0] + r[4] * be[1] + 2 * r[5] * be[2] + r[8] * be[3];
+        a[i][3] = r[6] * be[0] + r[7] * be[1] + r[8] * be[2] + 2 * r[9] * be[3];
+        b[i] = rho[i] - (r[0] * be[0] * be[0] + r[1] * be[0] * be[1] + r[2] * be[1] * be[1] +
+                         r[3] * be[0] * be[2] + r[4] * be[1] * be[2] + r[5] * be[2] * be[2] +
+                         r[6] * be[0] * be[3] + r[7] * be[1] * be[3] + r[8] * be[2] * be[3] +
+                         r[9] * be[3] * be[3]);
+      }
+      lstsq6<4>(a, b, x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) be[k] += x[k];
+    }
+    PoseRT cur;
+    compute_r_and_t(ws, be, al, pw, u, v, active, n, first_lane, pw0, cam, cur);
+    if (cand == 0 || cur.err < best.err) best = cur;
+  }
+}
+
+// cv::RNG (multiply-with-carry), seed (uint64)-1 as RANSACPointSetRegistrator::run uses
+struct CvRng {
+  unsigned long long state;
+  __device__ unsigned next() {
+    state = (unsigned long long)(unsigned)state * 4164903690ull + (state >> 32);
+    return (unsigned)state;
+  }
+  __device__ int uniform(int a, int b) { return a == b ? a : (int)(next() % (unsigned)(b - a) + a); }
+};
+
+__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmin(fmax(p, 0.0), 1.0);
+  ep = fmin(fmax(ep, 0.0), 1.0);
+  double num = fmax(1.0 - p, DBL_MIN);
+  double denom = 1.0 - pow(1.0 - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num); denom = log(denom);
+  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+
+// cv2.solvePnPRansac(flags=EPNP) restated (oracle/epnp_port.py solve_pnp_ransac_epnp).
+// pw/u/v are this lane's correspondence (already rounded to float32 by the caller, as
+// OpenCV converts its inputs to CV_32F).  Returns status; all lanes hold the same result.
+__device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw[3], double u, double v,
+                               const Cam& cam, double reproj_err, int max_iters, double confidence,
+                               PoseRT& out, unsigned& inlier_mask) {
+  const int model_points = 5;
+  inlier_mask = 0;
+  if (n < model_points) return EPB_POSE_TOO_FEW;
+  const unsigned all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  if (n == model_points) {
+    epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, out);
+    inlier_mask = all;
+    return EPB_POSE_OK;
+  }
+  CvRng rng{0xFFFFFFFFFFFFFFFFull};
+  int niters = max_iters;
+  unsigned best_mask = 0;
+  int best_count = 0;
+  const float thr2 = (float)(reproj_err * reproj_err);
+  for (int it = 0; it < niters; ++it) {
+    int idx[5];
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      int k = rng.uniform(0, n);
+      while (m & (1u << k)) k = rng.uniform(0, n);
+      idx[i] = k; m |= 1u << k;
+    }
+    PoseRT cur;
+    epnp_core(ws, lane, (m >> lane) & 1u, 5, idx[0], pw, u, v, cam, cur);
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) finite = finite && isfinite(cur.R[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) finite = finite && isfinite(cur.t[i]);
+    if (finite) {
+      const double xc = cur.R[0] * pw[0] + cur.R[1] * pw[1] + cur.R[2] * pw[2] + cur.t[0];
+      const double yc = cur.R[3] * pw[0] + cur.R[4] * pw[1] + cur.R[5] * pw[2] + cur.t[1];
+      const double zc = cur.R[6] * pw[0] + cur.R[7] * pw[1] + cur.R[8] * pw[2] + cur.t[2];
+      const double du = u - (cam.uc + cam.fu * xc / zc), dv = v - (cam.vc + cam.fv * yc / zc);
+      const bool good = lane < n && ((float)(du * du + dv * dv) <= thr2);
+      const unsigned gm = __ballot_sync(FULL, good);
+      const int cnt = __popc(gm);
+      if (cnt > max(best_count, model_points - 1)) {
+        best_mask = gm; best_count = cnt;
+        niters = ransac_update_num_iters(confidence, (double)(n - cnt) / n, model_points, niters);
+      }
+    }
+  }
+  if (best_mask == 0) return EPB_POSE_FAILED;
+  epnp_core(ws, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
+  inlier_mask = best_mask;
+  return EPB_POSE_OK;
+}
+
+// ------------------------------------------------------------------------------ rotations
+// cv2.Rodrigues, vector -> matrix
+__device__ void rodrigues_to_matrix(const double r[3], double R[9]) {
+  const double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  if (theta < DBL_EPSILON) {
+    R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+    return;
+  }
+  const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+  const double x = r[0] * it, y = r[1] * it, z = r[2] * it;
+  R[0] = c + c1 * x * x;     R[1] = c1 * x * y - s * z; R[2] = c1 * x * z + s * y;
+  R[3] = c1 * x * y + s * z; R[4] = c + c1 * y * y;     R[5] = c1 * y * z - s * x;
+  R[6] = c1 * x * z - s * y; R[7] = c1 * y * z + s * x; R[8] = c + c1 * z * z;
+}
+// cv2.Rodrigues, matrix -> vector (R assumed orthonormal; OpenCV first re-orthogonalises by SVD)
+__device__ void matrix_to_rodrigues(const double R[9], double r[3]) {
+  double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+  const double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+  double c = (R[0] + R[4] + R[8] - 1.0) * 0.5;
+  c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+  double theta = acos(c);
+  if (s < 1e-5) {
+    if (c > 0) { r[0] = r[1] = r[2] = 0.0; return; }
+    double t = (R[0] + 1) * 0.5; rx = sqrt(fmax(t, 0.0));
+    t = (R[4] + 1) * 0.5; ry = sqrt(fmax(t, 0.0)) * (R[1] < 0 ? -1.0 : 1.0);
+    t = (R[8] + 1) * 0.5; rz = sqrt(fmax(t, 0.0)) * (R[2] < 0 ? -1.0 : 1.0);
+    if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && ((R[5] > 0) != (ry * rz > 0))) rz = -rz;
+    theta /= sqrt(rx * rx + ry * ry + rz * rz);
+    r[0] = rx * theta; r[1] = ry * theta; r[2] = rz * theta;
+  } else {
+    const double vth = theta / (2.0 * s);
+    r[0] = rx * vth; r[1] = ry * vth; r[2] = rz * vth;
+  }
+}
+// scipy Rotation.from_matrix(R).as_quat() -> (x,y,z,w); returned as (w,x,y,z)
+__device__ void matrix_to_quat_wxyz(const double R[9], double q[4]) {
+  const double tr = R[0] + R[4] + R[8];
+  double x, y, z, w;
+  int choice = 0; double best = R[0];
+  if (R[4] > best) { best = R[4]; choice = 1; }
+  if (R[8] > best) { best = R[8]; choice = 2; }
+  if (tr > best) { choice = 3; }
+  if (choice == 0) { x = 1 - tr + 2 * R[0]; y = R[3] + R[1]; z = R[6] + R[2]; w = R[7] - R[5]; }
+  else if (choice == 1) { y = 1 - tr + 2 * R[4]; z = R[7] + R[5]; x = R[1] + R[3]; w = R[2] - R[6]; }
+  else if (choice == 2) { z = 1 - tr + 2 * R[8]; x = R[2] + R[6]; y = R[5] + R[7]; w = R[3] - R[1]; }
+  else { x = R[7] - R[5]; y = R[2] - R[6]; z = R[3] - R[1]; w = 1 + tr; }
+  const double inv = 1.0 / sqrt(x * x + y * y + z * z + w * w);
+  q[0] = w * inv; q[1] = x * inv; q[2] = y * inv; q[3] = z * inv;
+}
+
+// ------------------------------------------------------------------------------ LM (TinySolver recipe)
+struct J3 { double a, v0, v1, v2; };
+__device__ __forceinline__ J3 jc(double a) { return {a, 0, 0, 0}; }
+__device__ __forceinline__ J3 operator+(J3 x, J3 y) { return {x.a + y.a, x.v0 + y.v0, x.v1 + y.v1, x.v2 + y.v2}; }
+__device__ __forceinline__ J3 operator-(J3 x, J3 y) { return {x.a - y.a, x.v0 - y.v0, x.v1 - y.v1, x.v2 - y.v2}; }
+__device__ __forceinline__ J3 operator*(J3 x, J3 y) {
+  return {x.a * y.a, x.a * y.v0 + x.v0 * y.a, x.a * y.v1 + x.v1 * y.a, x.a * y.v2 + x.v2 * y.a};
+}
+__device__ __forceinline__ J3 operator*(J3 x, double s) { return {x.a * s, x.v0 * s, x.v1 * s, x.v2 * s}; }
+
+// rotation.h:563-620 with forward-mode duals on the angle-axis parameters
+__device__ void rotate_point_jet(const double aa[3], const double pt[3], J3 out[3]) {
+  const J3 w0 = {aa[0], 1, 0, 0}, w1 = {aa[1], 0, 1, 0}, w2 = {aa[2], 0, 0, 1};
+  const J3 theta2 = w0 * w0 + w1 * w1 + w2 * w2;
+  if (theta2.a > DBL_EPSILON) {
+    const double th = sqrt(theta2.a);
+    const double dth = 1.0 / (2.0 * th);
+    const J3 theta = {th, theta2.v0 * dth, theta2.v1 * dth, theta2.v2 * dth};
+    const double c = cos(th), s = sin(th);
+    const J3 ct = {c, -s * theta.v0, -s * theta.v1, -s * theta.v2};
+    const J3 st = {s, c * theta.v0, c * theta.v1, c * theta.v2};
+    const double ith = 1.0 / th, dith = -ith * ith;
+    const J3 ti = {ith, dith * theta.v0, dith * theta.v1, dith * theta.v2};
+    const J3 n0 = w0 * ti, n1 = w1 * ti, n2 = w2 * ti;
+    const J3 x0 = n1 * pt[2] - n2 * pt[1], x1 = n2 * pt[0] - n0 * pt[2], x2 = n0 * pt[1] - n1 * pt[0];
+    const J3 tmp = (n0 * pt[0] + n1 * pt[1] + n2 * pt[2]) * (jc(1.0) - ct);
+    out[0] = ct * pt[0] + x0 * st + n0 * tmp;
+    out[1] = ct * pt[1] + x1 * st + n1 * tmp;
+    out[2] = ct * pt[2] + x2 * st + n2 * tmp;
+  } else {
+    out[0] = jc(pt[0]) + (w1 * pt[2] - w2 * pt[1]);
+    out[1] = jc(pt[1]) + (w2 * pt[0] - w0 * pt[2]);
+    out[2] = jc(pt[2]) + (w0 * pt[1] - w1 * pt[0]);
+  }
+}
+
+// uncertainty_pnp.cpp:16-34: this lane's two residuals and (optionally) their 2x6 jacobian
+__device__ void residual_lane(const double x[6], const double pt[3], double u, double v, double wxx,
+                              double wxy, double wyy, const Cam& cam, bool active, double r[2],
+                              double (*J)[6]) {
+  if (!active) {
+    r[0] = r[1] = 0.0;
+    if (J) for (int k = 0; k < 6; ++k) { J[0][k] = 0.0; J[1][k] = 0.0; }
+    return;
+  }
+  J3 p[3];
+  rotate_point_jet(x, pt, p);
+  const double X = p[0].a + x[3], Y = p[1].a + x[4], Z = p[2].a + x[5];
+  const double iz = 1.0 / Z;
+  const double dx = cam.fu * X * iz + cam.uc - u, dy = cam.fv * Y * iz + cam.vc - v;
+  r[0] = wxx * dx + wxy * dy;
+  r[1] = wxy * dx + wyy * dy;
+  if (J) {
+    double jx[6], jy[6];
+    const double fxz = cam.fu * iz, fyz = cam.fv * iz, xz = X * iz, yz = Y * iz;
+    jx[0] = fxz * (p[0].v0 - xz * p[2].v0); jx[1] = fxz * (p[0].v1 - xz * p[2].v1); jx[2] = fxz * (p[0].v2 - xz * p[2].v2);
+    jy[0] = fyz * (p[1].v0 - yz * p[2].v0); jy[1] = fyz * (p[1].v1 - yz * p[2].v1); jy[2] = fyz * (p[1].v2 - yz * p[2].v2);
+    jx[3] = fxz; jx[4] = 0.0; jx[5] = -fxz * xz;
+    jy[3] = 0.0; jy[4] = fyz; jy[5] = -fyz * yz;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { J[0][k] = wxx * jx[k] + wxy * jy[k]; J[1][k] = wxy * jx[k] + wyy * jy[k]; }
+  }
+}
+
+__device__ bool ldlt_solve6(const double (&A)[6][6], const double (&b)[6], double (&x)[6]) {
+  double L[6][6], D[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+    D[j] = d;
+    if (d == 0.0 || d != d) ok = false;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = s / d;
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s; }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] /= D[i];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) { double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k]; x[i] = s; }
+  return ok;
+}
+
+struct LmState { double scale[6]; double jtj[6][6]; double g[6]; double cost, gmax; };
+
+// tiny_solver.h:166-195 (Update)
+__device__ void lm_update(const double x[6], const double pt[3], double u, double v, double wxx,
+                          double wxy, double wyy, const Cam& cam, bool active, bool first, LmState& S) {
+  double r[2], J[2][6];
+  residual_lane(x, pt, u, v, wxx, wxy, wyy, cam, active, r, J);
+  r[0] = -r[0]; r[1] = -r[1];
+  if (first) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) S.scale[k] = 1.0 / (1.0 + sqrt(warp_sum(J[0][k] * J[0][k] + J[1][k] * J[1][k])));
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { J[0][k] *= S.scale[k]; J[1][k] *= S.scale[k]; }
+  S.gmax = 0.0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+#pragma unroll
+    for (int b = a; b < 6; ++b) {
+      const double s = warp_sum(J[0][a] * J[0][b] + J[1][a] * J[1][b]);
+      S.jtj[a][b] = s; S.jtj[b][a] = s;
+    }
+    const double gg = warp_sum(J[0][a] * r[0] + J[1][a] * r[1]);
+    S.g[a] = gg; S.gmax = fmax(S.gmax, fabs(gg));
+  }
+  S.cost = 0.5 * warp_sum(r[0] * r[0] + r[1] * r[1]);
+}
+
+// tiny_solver.h:197-293 (Solve).  Returns TinySolver's status (0 gradient, 1 step, 2 cost, 3 max-iter).
+__device__ int lm_solve(double x[6], const double pt[3], double u, double v, double wxx, double wxy,
+                        double wyy, const Cam& cam, bool active, int* iterations, double* final_cost) {
+  LmState S;
+  int status = 3, it = 0;
+  lm_update(x, pt, u, v, wxx, wxy, wyy, cam, active, true, S);
+  if (S.gmax < 1e-10) status = 0;
+  else if (S.cost < DBL_EPSILON) status = 2;
+  else {
+    double uu = 1.0 / 1e4, vv = 2.0;
+    for (it = 1; it < 50; ++it) {
+      double A[6][6], step[6], dx[6], xn[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) A[i][j] = S.jtj[i][j];
+        const double dg = fmin(fmax(S.jtj[i][i], 1e-6), 1e32);
+        const double lm = sqrt(uu * dg);
+        A[i][i] += lm * lm;
+      }
+      const bool ok = ldlt_solve6(A, S.g, step);
+      double nx = 0, ndx = 0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { dx[i] = S.scale[i] * step[i]; nx += x[i] * x[i]; ndx += dx[i] * dx[i]; }
+      if (ok && sqrt(ndx) < 1e-8 * (sqrt(nx) + 1e-8)) { status = 1; break; }
+      double rho = -1.0;
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) xn[i] = x[i] + dx[i];
+        double r[2];
+        residual_lane(xn, pt, u, v, wxx, wxy, wyy, cam, active, r, nullptr);
+        const double f2 = warp_sum(r[0] * r[0] + r[1] * r[1]);
+        const double cost_change = 2 * S.cost - f2;
+        double model = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+          double s = 2 * S.g[a];
+#pragma unroll
+          for (int b = 0; b < 6; ++b) s -= S.jtj[a][b] * step[b];
+          model += step[a] * s;
+        }
+        rho = cost_change / model;
+      }
+      if (rho > 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = xn[i];
+        lm_update(x, pt, u, v, wxx, wxy, wyy, cam, active, false, S);
+        if (S.gmax < 1e-10) { status = 0; break; }
+        if (S.cost < DBL_EPSILON) { status = 2; break; }
+        const double tmp = 2 * rho - 1;
+        uu = uu * fmax(1 / 3., 1 - tmp * tmp * tmp);
+        vv = 2;
+        continue;
+      }
+      uu *= vv; vv *= 2;
+    }
+  }
+  if (iterations) *iterations = it;
+  if (final_cost) *final_cost = S.cost;
+  return status;
+}
+
+// ------------------------------------------------------------------------------ kernels
+__device__ __forceinline__ Cam load_cam(const double* K, int batched, int img) {
+  const double* k = K + (batched ? (size_t)img * 9 : 0);
+  return {k[0], k[4], k[2], k[5]};
+}
+__device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
+
+__global__ void __launch_bounds__(POSE_WARPS * 32)
+pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __restrict__ p2d,
+           const double* __restrict__ K, int K_batched, const int32_t* __restrict__ npts, int B,
+           int n_max, double reproj_err, int max_iters, double confidence, double* __restrict__ rt34,
+           unsigned long long* __restrict__ inlier_mask, int32_t* __restrict__ status) {
+  __shared__ WarpScratch scratch[POSE_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * POSE_WARPS + warp;
+  if (img >= B) return;
+  WarpScratch& ws = scratch[warp];
+  const int n = npts ? min(npts[img], n_max) : n_max;
+  double pw[3] = {0, 0, 0}, u = 0, v = 0;
+  if (lane < n) {
+    const double* q3 = p3d + ((p3d_batched ? (size_t)img * n_max : 0) + lane) * 3;
+    const double* q2 = p2d + ((size_t)img * n_max + lane) * 2;
+    // OpenCV's solvePnPRansac converts its inputs to CV_32F
+    pw[0] = round_f32(q3[0]); pw[1] = round_f32(q3[1]); pw[2] = round_f32(q3[2]);
+    u = round_f32(q2[0]); v = round_f32(q2[1]);
+  }
+  const Cam cam = load_cam(K, K_batched, img);
+  PoseRT out;
+  unsigned mask = 0;
+  const int st = pnp_ransac_epnp(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask);
+  if (lane == 0) {
+    double* o = rt34 + (size_t)img * 12;
+    if (st == EPB_POSE_OK) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { o[4 * i] = out.R[3 * i]; o[4 * i + 1] = out.R[3 * i + 1]; o[4 * i + 2] = out.R[3 * i + 2]; o[4 * i + 3] = out.t[i]; }
+    } else {
+      for (int i = 0; i < 12; ++i) o[i] = NAN;
+    }
+    if (inlier_mask) inlier_mask[img] = mask;
+    if (status) status[img] = st;
+  }
+}
+
+__global__ void __launch_bounds__(POSE_WARPS * 32)
+lm_kernel(const double* __restrict__ p2d, const double* __restrict__ p3d, int p3d_batched,
+          const double* __restrict__ w2d, const double* __restrict__ K, int K_batched,
+          const double* __restrict__ init_rt, const int32_t* __restrict__ npts, int B, int n_max,
+          double* __restrict__ result_rt, int32_t* __restrict__ iters, double* __restrict__ final_cost) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * POSE_WARPS + warp;
+  if (img >= B) return;
+  const int n = npts ? min(npts[img], n_max) : n_max;
+  const bool active = lane < n;
+  double pt[3] = {0, 0, 0}, u = 0, v = 0, wxx = 0, wxy = 0, wyy = 0;
+  if (active) {
+    const double* q3 = p3d + ((p3d_batched ? (size_t)img * n_max : 0) + lane) * 3;
+    const double* q2 = p2d + ((size_t)img * n_max + lane) * 2;
+    const double* qw = w2d + ((size_t)img * n_max + lane) * 3;
+    pt[0] = q3[0]; pt[1] = q3[1]; pt[2] = q3[2]; u = q2[0]; v = q2[1];
+    wxx = qw[0]; wxy = qw[1]; wyy = qw[2];
+  }
+  const Cam cam = load_cam(K, K_batched, img);
+  double x[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) x[k] = init_rt[(size_t)img * 6 + k];
+  int it = 0; double fc = 0;
+  lm_solve(x, pt, u, v, wxx, wxy, wyy, cam, active, &it, &fc);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) result_rt[(size_t)img * 6 + k] = x[k];
+    if (iters) iters[img] = it;
+    if (final_cost) final_cost[img] = fc;
+  }
+}
+
+__global__ void pose_pack_kernel(const double* __restrict__ rt6, int B, float* __restrict__ pose7,
+                                 double* __restrict__ rt34) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  double r[3] = {rt6[6 * i], rt6[6 * i + 1], rt6[6 * i + 2]}, R[9], q[4];
+  rodrigues_to_matrix(r, R);
+  if (pose7) {
+    matrix_to_quat_wxyz(R, q);
+    float* o = pose7 + 7 * (size_t)i;
+    o[0] = (float)q[0]; o[1] = (float)q[1]; o[2] = (float)q[2]; o[3] = (float)q[3];
+    o[4] = (float)rt6[6 * i + 3]; o[5] = (float)rt6[6 * i + 4]; o[6] = (float)rt6[6 * i + 5];
+  }
+  if (rt34) {
+    double* o = rt34 + 12 * (size_t)i;
+    for (int a = 0; a < 3; ++a) { o[4 * a] = R[3 * a]; o[4 * a + 1] = R[3 * a + 1]; o[4 * a + 2] = R[3 * a + 2]; o[4 * a + 3] = rt6[6 * i + 3 + a]; }
+  }
+}
+
+__global__ void rt34_to_rt6_kernel(const double* __restrict__ rt34, int B, double* __restrict__ rt6) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const double* m = rt34 + 12 * (size_t)i;
+  const double R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]};
+  double r[3];
+  matrix_to_rodrigues(R, r);
+  double* o = rt6 + 6 * (size_t)i;
+  o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = m[3]; o[4] = m[7]; o[5] = m[11];
+}
+
+// val.py:172-228 for a batch: one warp per frame, lane k <-> keypoint k (K <= 32)
+__global__ void __launch_bounds__(POSE_WARPS * 32)
+pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ maxvals,
+                     const double* __restrict__ bbox_xy, const double* __restrict__ rate,
+                     const double* __restrict__ p3d_model, const double* __restrict__ Kmat, int B, int K,
+                     int min_k, double sel_thresh, int weighted, float* __restrict__ pose7,
+                     double* __restrict__ rt6_out, double* __restrict__ epnp_rt34,
+                     int32_t* __restrict__ status) {
+  __shared__ WarpScratch scratch[POSE_WARPS];
+  __shared__ double s_pts[POSE_WARPS][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int img = blockIdx.x * POSE_WARPS + warp;
+  if (img >= B) return;
+  WarpScratch& ws = scratch[warp];
+  // --- keypoint selection (val.py:172-177): large_k = max(#(maxval > 0.8), 24), top large_k by maxval
+  const bool have = lane < K;
+  const float mv = have ? maxvals[(size_t)img * K + lane] : -INFINITY;
+  int large_k = __popc(__ballot_sync(FULL, have && (double)mv > sel_thresh));
+  large_k = min(max(large_k, min_k), K);
+  int rank = 0;
+  for (int j = 0; j < K; ++j) {
+    const float mj = __shfl_sync(FULL, mv, j);
+    rank += (mj > mv) || (mj == mv && j < lane);
+  }
+  // --- un-crop (val.py:180): float32 pred * (1/rate) + (x, y), in float64
+  if (have) {
+    const double inv_rate = 1.0 / rate[img];
+    double* d = s_pts[warp][rank];
+    d[0] = p3d_model[3 * lane]; d[1] = p3d_model[3 * lane + 1]; d[2] = p3d_model[3 * lane + 2];
+    d[3] = (double)preds[((size_t)img * K + lane) * 2] * inv_rate + bbox_xy[2 * img];
+    d[4] = (double)preds[((size_t)img * K + lane) * 2 + 1] * inv_rate + bbox_xy[2 * img + 1];
+    d[5] = (double)mv;
+  }
+  __syncwarp();
+  const int n = large_k;
+  const bool active = lane < n;
+  double pt[3] = {0, 0, 0}, u = 0, v = 0, w = 0;
+  if (active) {
+    const double* d = s_pts[warp][lane];
+    pt[0] = d[0]; pt[1] = d[1]; pt[2] = d[2]; u = d[3]; v = d[4]; w = d[5];
+  }
+  const Cam cam = {Kmat[0], Kmat[4], Kmat[2], Kmat[5]};
+  // --- pnp(): EPnP-RANSAC on float32-rounded correspondences
+  const double pwf[3] = {round_f32(pt[0]), round_f32(pt[1]), round_f32(pt[2])};
+  PoseRT init;
+  unsigned mask = 0;
+  const int st = pnp_ransac_epnp(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask);
+  double x[6];
+  if (st == EPB_POSE_OK) {
+    matrix_to_rodrigues(init.R, x);
+    x[3] = init.t[0]; x[4] = init.t[1]; x[5] = init.t[2];
+    if (epnp_rt34 && lane == 0) {
+      double* o = epnp_rt34 + 12 * (size_t)img;
+      for (int i = 0; i < 3; ++i) { o[4 * i] = init.R[3 * i]; o[4 * i + 1] = init.R[3 * i + 1]; o[4 * i + 2] = init.R[3 * i + 2]; o[4 * i + 3] = init.t[i]; }
+    }
+    // --- cpnp_m: LM with maxval weights on the unrounded float64 correspondences
+    const double ww = weighted ? w : 1.0;
+    lm_solve(x, pt, u, v, ww, 0.0, ww, cam, active, nullptr, nullptr);
+  } else {
+    for (int k = 0; k < 6; ++k) x[k] = NAN;
+    if (epnp_rt34 && lane == 0) for (int i = 0; i < 12; ++i) epnp_rt34[12 * (size_t)img + i] = NAN;
+  }
+  if (lane == 0) {
+    if (rt6_out) for (int k = 0; k < 6; ++k) rt6_out[6 * (size_t)img + k] = x[k];
+    if (pose7) {
+      double R[9], q[4];
+      rodrigues_to_matrix(x, R);
+      matrix_to_quat_wxyz(R, q);
+      float* o = pose7 + 7 * (size_t)img;
+      o[0] = (float)q[0]; o[1] = (float)q[1]; o[2] = (float)q[2]; o[3] = (float)q[3];
+      o[4] = (float)x[3]; o[5] = (float)x[4]; o[6] = (float)x[5];
+    }
+    if (status) status[img] = st;
+  }
+}
+
+// demo.py:295-310
+__global__ void esa_score_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int B,
+                                 double* __restrict__ score_t, double* __restrict__ score_r) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const float* p = pred + 7 * (size_t)i;
+  const float* g = gt + 7 * (size_t)i;
+  double dt = 0, nt = 0, dq = 0;
+  for (int k = 0; k < 3; ++k) {
+    const double d = (double)p[4 + k] - (double)g[4 + k];
+    dt += d * d; nt += (double)g[4 + k] * (double)g[4 + k];
+  }
+  // pred_qua is float32 and target float (np.matmul in the dtype numpy promotes to)
+  for (int k = 0; k < 4; ++k) dq += (double)p[k] * (double)g[k];
+  dq = fabs(dq);
+  if (score_t) score_t[i] = sqrt(dt) / sqrt(nt);
+  if (score_r) score_r[i] = dq > 1.0 ? 0.0 : 2.0 * acos(dq);  // Re(arccos(x + 0j)) = 0 for x > 1
+}
+
+}  // namespace epb
+
+using namespace epb;
+
+extern "C" int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const double* p2d, const double* K,
+                                   int K_batched, const int32_t* npts, int B, int n_max, double reproj_err,
+                                   int max_iters, double confidence, double* rt34,
+                                   unsigned long long* inlier_mask, int32_t* status, void* stream) {
+  if (!p3d || !p2d || !K || !rt34 || B < 0 || n_max <= 0 || n_max > 32 || max_iters < 0) return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  pnp_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      p3d, p3d_batched, p2d, K, K_batched, npts, B, n_max, reproj_err, max_iters, confidence, rt34,
+      inlier_mask, status);
+  return check_launch();
+}
+
+extern "C" int epb_lm_refine(const double* p2d, const double* p3d, int p3d_batched, const double* w2d,
+                             const double* K, int K_batched, const double* init_rt, const int32_t* npts,
+                             int B, int n_max, double* result_rt, int32_t* iters, double* final_cost,
+                             void* stream) {
+  if (!p2d || !p3d || !w2d || !K || !init_rt || !result_rt || B < 0 || n_max <= 0 || n_max > 32)
+    return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  lm_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      p2d, p3d, p3d_batched, w2d, K, K_batched, init_rt, npts, B, n_max, result_rt, iters, final_cost);
+  return check_launch();
+}
+
+extern "C" int epb_pose_pack(const double* rt6, int B, float* pose7, double* rt34, void* stream) {
+  if (!rt6 || B < 0 || (!pose7 && !rt34)) return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  pose_pack_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rt6, B, pose7, rt34);
+  return check_launch();
+}
+
+extern "C" int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* stream) {
+  if (!rt34 || !rt6 || B < 0) return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  rt34_to_rt6_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rt34, B, rt6);
+  return check_launch();
+}
+
+extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const double* bbox_xy,
+                                 const double* rate, const double* p3d_model, const double* Kmat, int B,
+                                 int K, int min_k, double sel_thresh, int weighted, float* pose7, double* rt6,
+                                 double* epnp_rt34, int32_t* status, void* stream) {
+  if (!preds || !maxvals || !bbox_xy || !rate || !p3d_model || !Kmat || B < 0 || K <= 0 || K > 32)
+    return EPB_ERR_INVALID;
+  if (!pose7 && !rt6) return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  pose_pipeline_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6,
+      epnp_rt34, status);
+  return check_launch();
+}
+
+extern "C" int epb_esa_score(const float* pose7_pred, const float* pose7_gt, int B, double* score_t,
+                             double* score_r, void* stream) {
+  if (!pose7_pred || !pose7_gt || B < 0) return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  esa_score_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pose7_pred, pose7_gt, B, score_t, score_r);
+  return check_launch();
+}

@@ -1,0 +1,1076 @@
+// PVNet-style RANSAC keypoint voting for sm_100a, batched and stream-ordered.
+//
+// Replaces (paths under /root/reference/lib/ransac_voting_gpu_layer):
+//   src/ransac_voting_kernel.cu:11-49   generate_hypothesis_kernel
+//   src/ransac_voting_kernel.cu:88-126  voting_for_hypothesis_kernel  (+ the hn*vn*tn byte tensor
+//                                        and torch.sum that follow it, ransac_voting_gpu.py:557-561)
+//   ransac_voting_gpu.py:514-598 v3, :669-761 v4, :763-858 v5, :218-261 hypothesis,
+//   :263-331 / :333-406 voting distribution (the per-image Python loops, torch.nonzero /
+//   masked_select compaction, uniform_/random_ draws, torch.max / topk / matmul / solve tails).
+//
+// Pipeline of one epb_voting_run() call (no host synchronisation anywhere):
+//   mask_count -> mask_scan -> rng_offsets -> [mask_count/scan with the max_num subsample]
+//   -> mask_scatter (stable row-major compaction of foreground pixel coordinates)
+//   -> hypothesis (seeded pairs of foreground pixels -> ray intersections)
+//   -> vote_count (dominant: hn*vn*tn inlier tests per image, never materialised)
+//   -> winner_refine | distribution.
+//
+// Bit-exactness: every float operation of the reference kernels is issued through explicit
+// round-to-nearest intrinsics in the order the reference SASS executes them, so
+// nvcc cannot re-contract them.  vote_count decides each (hypothesis, pixel) pair with a
+// division/sqrt-free squared-cosine test whose error bound is proven in DESIGN.md; only pairs
+// within 2^-20 of the threshold fall through to the exact IEEE path, so the counts equal the
+// reference's integers.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace epb {
+
+// ------------------------------------------------------------------------------------------
+// exact reference arithmetic
+// ------------------------------------------------------------------------------------------
+
+// ransac_voting_kernel.cu:22-48 as compiled (SASS of the shipped cubin):
+//   det1 = rn(nx1*ny0) - rn(nx0*ny1), det2 = -det1, guards in double,
+//   s = fma(nx,cx,rn(ny*cy)), y = fma(nx1,s0,-rn(nx0*s1))/det1, x = fma(ny1,s0,-rn(ny0*s1))/det2
+__device__ __forceinline__ bool intersect_rays(float dx0, float dy0, float cx0, float cy0,
+                                               float dx1, float dy1, float cx1, float cy1,
+                                               float* x, float* y) {
+  const float nx0 = dy0, ny0 = -dx0, nx1 = dy1, ny1 = -dx1;
+  const float a = __fmul_rn(nx1, ny0);
+  const float b = __fmul_rn(nx0, ny1);
+  const float det1 = __fsub_rn(a, b);
+  const float det2 = __fsub_rn(b, a);
+  if (fabs((double)det1) < 1e-6) return false;
+  if (fabs((double)det2) < 1e-6) return false;
+  const float s0 = __fmaf_rn(nx0, cx0, __fmul_rn(ny0, cy0));
+  const float s1 = __fmaf_rn(nx1, cx1, __fmul_rn(ny1, cy1));
+  *y = __fdiv_rn(__fmaf_rn(nx1, s0, -__fmul_rn(nx0, s1)), det1);
+  *x = __fdiv_rn(__fmaf_rn(ny1, s0, -__fmul_rn(ny0, s1)), det2);
+  return true;
+}
+
+// ransac_voting_kernel.cu:100-125 as compiled (PTX pins the fma placement).
+__device__ __forceinline__ bool vote_exact(float cx, float cy, float nx, float ny, float norm1,
+                                           float hx, float hy, float thresh) {
+  const float dx = __fsub_rn(hx, cx);
+  const float dy = __fsub_rn(hy, cy);
+  const float norm2 = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+  if ((double)norm1 < 1e-6 || (double)norm2 < 1e-6) return false;
+  const float ad = __fdiv_rn(__fmaf_rn(dx, nx, __fmul_rn(dy, ny)), __fmul_rn(norm1, norm2));
+  return ad > thresh;
+}
+__device__ __forceinline__ float dir_norm(float nx, float ny) {
+  return __fsqrt_rn(__fmaf_rn(nx, nx, __fmul_rn(ny, ny)));
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 in the layout of torch's CUDA distribution kernels
+// (ATen/native/cuda/DistributionTemplates.h: block 256, grid = min(SMs * maxThreads/256,
+//  ceil(numel/256)), unroll 4, curand_init(seed, thread, offset)).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct TorchRngLayout {
+  unsigned total_threads;  // 256 * grid
+  unsigned long long inc;  // generator offset consumed by one call
+};
+__host__ __device__ inline TorchRngLayout torch_rng_layout(unsigned long long numel, int sm_count,
+                                                           int threads_per_sm) {
+  unsigned long long grid = (numel + 255) / 256;
+  const unsigned long long cap = (unsigned long long)sm_count * (unsigned)(threads_per_sm / 256);
+  if (grid > cap) grid = cap;
+  if (grid == 0) grid = 1;
+  TorchRngLayout l;
+  l.total_threads = (unsigned)(256 * grid);
+  l.inc = numel ? ((numel - 1) / (256ull * grid * 4ull) + 1ull) * 4ull : 0ull;
+  return l;
+}
+// raw 32-bit draw that element `li` of a torch CUDA tensor filled by one RNG call receives
+__device__ __forceinline__ unsigned torch_philox_u32(unsigned long long seed, unsigned long long offset,
+                                                     unsigned long long li, unsigned total_threads) {
+  const unsigned long long per_iter = 4ull * total_threads;
+  const unsigned long long k = li / per_iter;
+  const unsigned rem = (unsigned)(li - k * per_iter);
+  const unsigned ii = rem / total_threads;
+  const unsigned idx = rem - ii * total_threads;
+  const unsigned long long ctr = offset / 4ull + k;
+  const uint4 c = make_uint4((unsigned)ctr, (unsigned)(ctr >> 32), idx, 0u);
+  const uint4 r = philox4x32_10(c, make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+  return ii == 0 ? r.x : ii == 1 ? r.y : ii == 2 ? r.z : r.w;
+}
+// torch uniform_(0,1) on float32: curand_uniform (0,1] then 1.0 -> 0.0
+__device__ __forceinline__ float torch_uniform01(unsigned r) {
+  const float u = __fmaf_rn((float)r, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  return u == 1.0f ? 0.0f : u;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------
+constexpr int TILE_PX = 4096;  // 256 threads x 16 mask bytes
+
+struct Workspace {
+  int32_t* tile_counts;   // [B][T]
+  int32_t* tile_offsets;  // [B][T]
+  int32_t* fg;            // [B] foreground before the subsample
+  int32_t* tn;            // [B] after
+  int32_t* sub;           // [B] 1 if the max_num subsample applies
+  int32_t* live;          // [B] fg >= min_num
+  float* ratio;           // [B] max_num / fg (float32 like the reference)
+  unsigned long long* off_u;  // [B] generator offset of the uniform_ draw
+  unsigned long long* off_r;  // [B] generator offset of the first random_ draw
+  uint32_t* fgpix;        // [B][H*W] packed (y << 16 | x), row-major stable order
+  float2* hyp;            // [B][vn][HN]
+  int32_t* counts;        // [B][vn][HN]
+  size_t bytes;
+};
+__host__ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+__host__ inline Workspace carve(const epb_voting_params& p, void* base) {
+  Workspace w;
+  const size_t B = p.B, T = ((size_t)p.H * p.W + TILE_PX - 1) / TILE_PX;
+  const size_t HN = (size_t)p.hn * p.rounds;
+  char* c = (char*)base;
+  size_t o = 0;
+  auto take = [&](size_t n) { char* r = c + o; o += align_up(n); return (void*)r; };
+  w.tile_counts = (int32_t*)take(B * T * 4);
+  w.tile_offsets = (int32_t*)take(B * T * 4);
+  w.fg = (int32_t*)take(B * 4);
+  w.tn = (int32_t*)take(B * 4);
+  w.sub = (int32_t*)take(B * 4);
+  w.live = (int32_t*)take(B * 4);
+  w.ratio = (float*)take(B * 4);
+  w.off_u = (unsigned long long*)take(B * 8);
+  w.off_r = (unsigned long long*)take(B * 8);
+  w.fgpix = (uint32_t*)take(B * (size_t)p.H * p.W * 4);
+  w.hyp = (float2*)take(B * p.vn * HN * 8);
+  w.counts = (int32_t*)take(B * p.vn * HN * 4);
+  w.bytes = o;
+  return w;
+}
+
+__device__ __forceinline__ bool mask_pred(unsigned m, int mask_mode) {
+  return mask_mode == EPB_MASK_EQ1 ? (m == 1u) : (m != 0u);
+}
+
+// foreground predicate of pixel `p` of image `b` including the optional max_num subsample
+// (ransac_voting_gpu.py:536-540: selection.uniform_(0,1) < max_num / fg.float())
+struct SubsampleCtx {
+  const float* selection;  // optional user draws [B][H*W]
+  unsigned long long seed;
+  unsigned total_threads;
+  int use_philox;
+};
+__device__ __forceinline__ bool keep_pixel(const SubsampleCtx& sc, int b, size_t hw, size_t p,
+                                           float ratio, unsigned long long off_u) {
+  float u;
+  if (sc.selection) u = __ldg(sc.selection + (size_t)b * hw + p);
+  else if (sc.use_philox) u = torch_uniform01(torch_philox_u32(sc.seed, off_u, p, sc.total_threads));
+  else return true;
+  return u < ratio;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. mask_count: per-tile foreground counts.  phase 0: plain mask; phase 1: with subsample,
+//    only for images flagged in ws.sub.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_count_kernel(const uint8_t* __restrict__ mask, int HW, int T, int mask_mode, int phase,
+                  Workspace ws, SubsampleCtx sc) {
+  const int b = blockIdx.y, tile = blockIdx.x;
+  if (phase == 1 && !ws.sub[b]) return;
+  const uint8_t* m = mask + (size_t)b * HW;
+  const int p0 = tile * TILE_PX + threadIdx.x * 16;
+  int cnt = 0;
+  float ratio = 0.f;
+  unsigned long long off_u = 0;
+  if (phase == 1) { ratio = ws.ratio[b]; off_u = ws.off_u[b]; }
+  if (p0 < HW) {
+    unsigned char bytes[16];
+    if (p0 + 16 <= HW && ((reinterpret_cast<uintptr_t>(m + p0) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(bytes) = __ldg(reinterpret_cast<const uint4*>(m + p0));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bytes[j] = (p0 + j < HW) ? m[p0 + j] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      bool f = (p0 + j < HW) && mask_pred(bytes[j], mask_mode);
+      if (f && phase == 1) f = keep_pixel(sc, b, HW, p0 + j, ratio, off_u);
+      cnt += f;
+    }
+  }
+  cnt = warp_sum_i(cnt);
+  __shared__ int s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i];
+    ws.tile_counts[(size_t)b * T + tile] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. mask_scan: one CTA per image, exclusive scan of the tile counts.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_scan_kernel(int T, int phase, int min_num, int max_num, int allow_sub, Workspace ws) {
+  const int b = blockIdx.x;
+  if (phase == 1 && !ws.sub[b]) return;
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int32_t* cnt = ws.tile_counts + (size_t)b * T;
+  int32_t* off = ws.tile_offsets + (size_t)b * T;
+  for (int base = 0; base < T; base += 256) {
+    const int i = base + threadIdx.x;
+    const int v = i < T ? cnt[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_warp[w];
+    const int carry = s_carry;
+    if (i < T) off[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int total = s_carry;
+    if (phase == 0) {
+      ws.fg[b] = total;
+      const int live = total >= min_num;
+      const int sub = live && allow_sub && total > max_num;
+      ws.live[b] = live;
+      ws.sub[b] = sub;
+      ws.ratio[b] = sub ? __fdiv_rn((float)max_num, (float)total) : 2.0f;
+      ws.tn[b] = live ? total : 0;
+    } else {
+      ws.tn[b] = total;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. rng_offsets: sequential (batch-order) generator offsets, exactly the order in which the
+//    reference's per-image loop consumes torch's generator: [uniform_ if fg > max_num],
+//    then `rounds` x random_.
+// ------------------------------------------------------------------------------------------
+__global__ void rng_offsets_kernel(int B, int rounds, unsigned long long base, unsigned long long inc_u,
+                                   unsigned long long inc_r, Workspace ws,
+                                   unsigned long long* consumed, int32_t* tn_out_unused) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long o = base;
+  for (int b = 0; b < B; ++b) {
+    ws.off_u[b] = o;
+    if (ws.sub[b]) o += inc_u;
+    ws.off_r[b] = o;
+    if (ws.live[b]) o += inc_r * (unsigned long long)rounds;
+  }
+  if (consumed) *consumed = o - base;
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. mask_scatter: stable compaction of foreground pixel coordinates.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int mask_mode,
+                    Workspace ws, SubsampleCtx sc) {
+  const int b = blockIdx.y, tile = blockIdx.x;
+  if (!ws.live[b]) return;
+  const int HW = H * W;
+  const uint8_t* m = mask + (size_t)b * HW;
+  const int p0 = tile * TILE_PX + threadIdx.x * 16;
+  const bool sub = ws.sub[b] != 0;
+  const float ratio = ws.ratio[b];
+  const unsigned long long off_u = ws.off_u[b];
+  unsigned flags = 0;
+  if (p0 < HW) {
+    unsigned char bytes[16];
+    if (p0 + 16 <= HW && ((reinterpret_cast<uintptr_t>(m + p0) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(bytes) = __ldg(reinterpret_cast<const uint4*>(m + p0));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bytes[j] = (p0 + j < HW) ? m[p0 + j] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      bool f = (p0 + j < HW) && mask_pred(bytes[j], mask_mode);
+      if (f && sub) f = keep_pixel(sc, b, HW, p0 + j, ratio, off_u);
+      flags |= (unsigned)f << j;
+    }
+  }
+  const int mine = __popc(flags);
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(FULL, incl, d);
+    if ((threadIdx.x & 31) >= d) incl += o;
+  }
+  __shared__ int s_warp[8];
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_warp[w];
+  int o = ws.tile_offsets[(size_t)b * T + tile] + wbase + incl - mine;
+  uint32_t* out = ws.fgpix + (size_t)b * HW;
+  while (flags) {
+    const int j = __ffs(flags) - 1;
+    flags &= flags - 1;
+    const int p = p0 + j;
+    const int y = p / W, x = p - y * W;
+    out[o++] = ((uint32_t)y << 16) | (uint32_t)x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 5. hypothesis generation (fused batched form of generate_hypothesis_kernel + idxs draw)
+// ------------------------------------------------------------------------------------------
+struct HypCtx {
+  const int32_t* idxs;  // IDXS / RAW32
+  int rng_mode;
+  unsigned long long seed;
+  unsigned total_threads_r;
+  unsigned long long inc_r;
+};
+__global__ void __launch_bounds__(256)
+hypothesis_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws, HypCtx hc,
+                  float* __restrict__ hyp_out) {
+  const int HN = p.hn * p.rounds;
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long per_img = (long long)HN * p.vn;
+  if (gid >= per_img * p.B) return;
+  const int b = (int)(gid / per_img);
+  const int rem = (int)(gid - (long long)b * per_img);
+  const int hh = rem / p.vn;  // hypothesis index over all rounds
+  const int v = rem - hh * p.vn;
+  const int r = hh / p.hn, h = hh - r * p.hn;
+  float x = 0.f, y = 0.f;
+  const int tn = ws.tn[b];
+  if (ws.live[b] && tn > 0) {
+    const size_t e = ((size_t)h * p.vn + v) * 2;  // element index inside one [hn,vn,2] draw
+    unsigned t0, t1;
+    if (hc.rng_mode == EPB_RNG_PHILOX) {
+      const unsigned long long off = ws.off_r[b] + hc.inc_r * (unsigned long long)r;
+      t0 = torch_philox_u32(hc.seed, off, e, hc.total_threads_r) % (unsigned)tn;
+      t1 = torch_philox_u32(hc.seed, off, e + 1, hc.total_threads_r) % (unsigned)tn;
+    } else {
+      const int32_t* q = hc.idxs + (((size_t)b * p.rounds + r) * p.hn) * p.vn * 2 + e;
+      t0 = (unsigned)q[0];
+      t1 = (unsigned)q[1];
+      if (hc.rng_mode == EPB_RNG_RAW32) { t0 %= (unsigned)tn; t1 %= (unsigned)tn; }
+      else { t0 = min(t0, (unsigned)tn - 1); t1 = min(t1, (unsigned)tn - 1); }
+    }
+    const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
+    const uint32_t q0 = fp[t0], q1 = fp[t1];
+    const int x0 = q0 & 0xffff, y0 = q0 >> 16, x1 = q1 & 0xffff, y1 = q1 >> 16;
+    const float* d0 = vertex + b * p.sb + y0 * p.sy + x0 * p.sx + v * p.sv;
+    const float* d1 = vertex + b * p.sb + y1 * p.sy + x1 * p.sx + v * p.sv;
+    float ix, iy;
+    if (intersect_rays(__ldg(d0), __ldg(d0 + p.sc), (float)x0, (float)y0, __ldg(d1), __ldg(d1 + p.sc),
+                       (float)x1, (float)y1, &ix, &iy)) {
+      x = ix; y = iy;
+    }
+  }
+  ws.hyp[((size_t)b * p.vn + v) * HN + hh] = make_float2(x, y);
+  if (hyp_out) {
+    float2* o = reinterpret_cast<float2*>(hyp_out) + ((size_t)b * HN + hh) * p.vn + v;
+    *o = make_float2(x, y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 6. vote_count: the dominant kernel.
+//
+// CTA = 128 threads, one (image, keypoint, chunk of 128*R hypotheses, pixel split).  Each thread
+// keeps R hypotheses and their counters in registers (lanes <-> hypotheses); foreground pixels
+// are staged through shared memory as 32-byte records and broadcast to all lanes, so every
+// (hypothesis, pixel) test costs ~12 issue slots instead of the reference's ~35 and nothing
+// but the field itself is read from memory.  The next tile's global gathers are issued before
+// the current tile is consumed (register prefetch, one __syncthreads per tile).
+//
+// Record: {cx, cy, nx, ny, cHi, cLo, g, norm1}
+//   s1 = |n|^2 as the reference rounds it, norm1 = sqrt.rn(s1)
+//   cHi = ru(T^2 s1 (1+2^-20)), cLo = rd(T^2 s1 (1-2^-20)), g = ru(4.1e-12 s1)
+// Test for hypothesis (hx,hy) with dx,dy,s2,dot exactly as the reference rounds them:
+//   dd = rn(dot*|dot|)
+//   dd >  fma(s2,cHi,g)  => reference says inlier      (voting error bound)
+//   dd <  rn(s2*cLo)     => reference says not inlier
+//   otherwise            => evaluate the reference expression (IEEE sqrt, div) exactly.
+// ------------------------------------------------------------------------------------------
+constexpr int VOTE_THREADS = 128;
+constexpr int VOTE_TILE = 512;  // records per smem tile
+struct __align__(16) VoteRec { float cx, cy, nx, ny, cHi, cLo, g, n1; };
+
+template <int R>
+__global__ void __launch_bounds__(VOTE_THREADS)
+vote_count_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws, int splits,
+                  int use_atomic) {
+  __shared__ VoteRec tile[2][VOTE_TILE];
+  const int HN = p.hn * p.rounds;
+  const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
+  const int b = blockIdx.z;
+  const int v = blockIdx.y / chunks, chunk = blockIdx.y - v * chunks;
+  const int split = blockIdx.x;
+  if (!ws.live[b]) return;
+  const int tn = ws.tn[b];
+  const int per = (tn + splits - 1) / splits;
+  const int t_begin = split * per, t_end = min(tn, t_begin + per);
+  if (t_begin >= t_end && use_atomic) return;
+
+  const float T = p.inlier_thresh;
+  const bool fast_ok = T >= 0.0009765625f && T < 1e18f;
+  const float T2u = __fmul_ru(T, T), T2d = __fmul_rd(T, T);
+  const float kHi = 1.0f + 9.5367431640625e-07f, kLo = 1.0f - 9.5367431640625e-07f;
+
+  float hx[R], hy[R];
+  int cnt[R];
+  const float2* hyp = ws.hyp + ((size_t)b * p.vn + v) * HN;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int h = chunk * VOTE_THREADS * R + r * VOTE_THREADS + threadIdx.x;
+    const float2 q = h < HN ? hyp[h] : make_float2(0.f, 0.f);
+    hx[r] = q.x; hy[r] = q.y; cnt[r] = 0;
+  }
+
+  const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
+  const float* vbase = vertex + b * p.sb + v * p.sv;
+  constexpr int PER_THREAD = VOTE_TILE / VOTE_THREADS;  // 4
+  uint32_t pq[PER_THREAD];
+  float pnx[PER_THREAD], pny[PER_THREAD];
+
+  auto prefetch = [&](int t0) {
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+      const int t = t0 + k * VOTE_THREADS + threadIdx.x;
+      if (t < t_end) {
+        const uint32_t q = __ldg(fp + t);
+        const float* d = vbase + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
+        pq[k] = q; pnx[k] = __ldg(d); pny[k] = __ldg(d + p.sc);
+      } else { pq[k] = 0xffffffffu; pnx[k] = 0.f; pny[k] = 0.f; }
+    }
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+      VoteRec rec;
+      const uint32_t q = pq[k];
+      rec.cx = (float)(q & 0xffff); rec.cy = (float)(q >> 16);
+      rec.nx = pnx[k]; rec.ny = pny[k];
+      const float s1 = __fmaf_rn(rec.nx, rec.nx, __fmul_rn(rec.ny, rec.ny));
+      rec.n1 = __fsqrt_rn(s1);
+      const bool valid = q != 0xffffffffu && !((double)rec.n1 < 1e-6) && (s1 == s1);
+      if (valid && fast_ok) {
+        rec.cHi = __fmul_ru(__fmul_ru(T2u, s1), kHi);
+        rec.cLo = __fmul_rd(__fmul_rd(T2d, s1), kLo);
+        rec.g = __fmul_ru(s1, 4.1e-12f);
+      } else if (valid) {  // threshold outside the proven range: always take the exact path
+        rec.cHi = INFINITY; rec.cLo = -INFINITY; rec.g = 0.f;
+      } else {             // padding / zero direction: never an inlier (reference guard :121)
+        rec.cHi = INFINITY; rec.cLo = INFINITY; rec.g = 0.f; rec.n1 = 0.f;
+        rec.cx = 0.f; rec.cy = 0.f; rec.nx = 0.f; rec.ny = 0.f;
+      }
+      tile[buf][k * VOTE_THREADS + threadIdx.x] = rec;
+    }
+  };
+
+  int buf = 0;
+  prefetch(t_begin);
+  stage(0);
+  __syncthreads();
+  for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE) {
+    const bool more = t0 + VOTE_TILE < t_end;
+    if (more) prefetch(t0 + VOTE_TILE);
+    const int nrec = min(VOTE_TILE, t_end - t0);
+    const VoteRec* rp = tile[buf];
+#pragma unroll 2
+    for (int i = 0; i < nrec; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(&rp[i].cx);
+      const float4 c = *reinterpret_cast<const float4*>(&rp[i].cHi);
+      bool amb = false;
+      bool in[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float dx = __fsub_rn(hx[r], a.x);
+        const float dy = __fsub_rn(hy[r], a.y);
+        const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+        const float dot = __fmaf_rn(dx, a.z, __fmul_rn(dy, a.w));
+        const float dd = __fmul_rn(dot, fabsf(dot));
+        const float mhi = __fmaf_rn(s2, c.x, c.z);
+        const float mlo = __fmul_rn(s2, c.y);
+        in[r] = dd > mhi;
+        amb |= !(dd > mhi) && !(dd < mlo);
+      }
+      if (amb) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) in[r] = vote_exact(a.x, a.y, a.z, a.w, c.w, hx[r], hy[r], T);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) cnt[r] += in[r];
+    }
+    if (more) stage(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int h = chunk * VOTE_THREADS * R + r * VOTE_THREADS + threadIdx.x;
+    if (h < HN) {
+      if (use_atomic) atomicAdd(out + h, cnt[r]);
+      else out[h] = cnt[r];
+    }
+  }
+}
+
+// counts_ws [B][vn][HN] -> user layout [B][HN][vn]
+__global__ void counts_export_kernel(epb_voting_params p, Workspace ws, int32_t* __restrict__ out) {
+  const int HN = p.hn * p.rounds;
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long n = (long long)p.B * HN * p.vn;
+  if (gid >= n) return;
+  const int v = (int)(gid % p.vn);
+  const long long r = gid / p.vn;
+  const int h = (int)(r % HN);
+  const int b = (int)(r / HN);
+  // degenerate images: the reference emits ones (ransac_voting_gpu.py:231)
+  out[gid] = ws.live[b] ? ws.counts[((size_t)b * p.vn + v) * HN + h] : 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// block reductions
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void block_sum_d(double (&v)[N], double* smem /* [N*8] */) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < N; ++i) smem[i * 8 + warp] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += smem[i * 8 + w];
+    v[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 7. winner selection + least-squares refinement (+ variance / confidence)
+//    ransac_voting_gpu.py:561-569 (first max, ratio = count/tn, strict '<' update from zeros)
+//    and :578-595 (re-vote the winner, 2x2 normal equations).  Sums in FP64.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+winner_refine_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws,
+                     float* __restrict__ pts, float* __restrict__ var_or_conf,
+                     int32_t* __restrict__ status) {
+  const int v = blockIdx.x, b = blockIdx.y;
+  const int HN = p.hn * p.rounds;
+  float2* out = reinterpret_cast<float2*>(pts) + (size_t)b * p.vn + v;
+  float* aux = var_or_conf ? var_or_conf + (size_t)b * p.vn + v : nullptr;
+  int32_t* st = status ? status + (size_t)b * p.vn + v : nullptr;
+  if (!ws.live[b]) {
+    if (threadIdx.x == 0) {
+      *out = make_float2(0.f, 0.f);
+      if (aux) *aux = p.mode == EPB_VOTE_V4 ? 1.0f : 0.0f;
+      if (st) *st = 1;
+    }
+    return;
+  }
+  __shared__ int s_cnt[8], s_idx[8];
+  __shared__ double s_red[7 * 8];
+  __shared__ float2 s_pt;
+  const int tn = ws.tn[b];
+  // first maximum of the counts
+  const int32_t* cnt = ws.counts + ((size_t)b * p.vn + v) * HN;
+  int bc = -1, bi = 0x7fffffff;
+  for (int h = threadIdx.x; h < HN; h += 256) {
+    const int c = cnt[h];
+    if (c > bc) { bc = c; bi = h; }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const int oc = __shfl_xor_sync(FULL, bc, m), oi = __shfl_xor_sync(FULL, bi, m);
+    if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_cnt[threadIdx.x >> 5] = bc; s_idx[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_cnt[w] > bc || (s_cnt[w] == bc && s_idx[w] < bi)) { bc = s_cnt[w]; bi = s_idx[w]; }
+    const float ratio = __fdiv_rn((float)bc, (float)tn);
+    // all_win_ratio starts at 0 and is replaced only where 0 < ratio (:566-569)
+    s_pt = (0.0f < ratio) ? ws.hyp[((size_t)b * p.vn + v) * HN + bi] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const float2 win = s_pt;
+  const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
+  const float* vbase = vertex + b * p.sb + v * p.sv;
+  // pass 1: inliers of the winner and the normal equations
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};  // a00 a01 a11 b0 b1 sum(bb^2) count
+  for (int t = threadIdx.x; t < tn; t += 256) {
+    const uint32_t q = __ldg(fp + t);
+    const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
+    const float* d = vbase + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
+    const float dx = __ldg(d), dy = __ldg(d + p.sc);
+    if (vote_exact(cx, cy, dx, dy, dir_norm(dx, dy), win.x, win.y, p.inlier_thresh)) {
+      const double nx = dy, ny = -(double)dx;  // normal = (d_y, -d_x), :580-581
+      const double bb = nx * cx + ny * cy;
+      acc[0] += nx * nx; acc[1] += nx * ny; acc[2] += ny * ny;
+      acc[3] += nx * bb; acc[4] += ny * bb; acc[5] += bb * bb; acc[6] += 1.0;
+    }
+  }
+  block_sum_d<7>(acc, s_red);
+  const double det = acc[0] * acc[2] - acc[1] * acc[1];
+  const bool singular = !(fabs(det) > 0.0) || !isfinite(det);
+  double px = NAN, py = NAN;
+  if (!singular) {
+    px = (acc[2] * acc[3] - acc[1] * acc[4]) / det;
+    py = (acc[0] * acc[4] - acc[1] * acc[3]) / det;
+  }
+  const float fxp = (float)px, fyp = (float)py;
+  if (threadIdx.x == 0) {
+    *out = make_float2(fxp, fyp);
+    if (st) *st = singular ? 2 : 0;
+    if (p.mode == EPB_VOTE_V4 && aux) {
+      // var = sum(residual^2) / sum(inlier), residual = n.pt - b   (:752-753)
+      const double rss = px * (acc[0] * px + acc[1] * py) + py * (acc[1] * px + acc[2] * py) -
+                         2.0 * (px * acc[3] + py * acc[4]) + acc[5];
+      *aux = (float)(fmax(rss, 0.0) / acc[6]);
+    }
+  }
+  if (p.mode == EPB_VOTE_V5 && aux) {
+    // confidence = share of pixels voting for the refined point at the literal 0.999 (:848-850)
+    int c = 0;
+    for (int t = threadIdx.x; t < tn; t += 256) {
+      const uint32_t q = __ldg(fp + t);
+      const float* d = vbase + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
+      const float dx = __ldg(d), dy = __ldg(d + p.sc);
+      c += vote_exact((float)(q & 0xffff), (float)(q >> 16), dx, dy, dir_norm(dx, dy), fxp, fyp, 0.999f);
+    }
+    double cc[1] = {(double)c};
+    block_sum_d<1>(cc, s_red);
+    if (threadIdx.x == 0) *aux = __fdiv_rn((float)(int)cc[0], (float)tn);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 8. voting distribution: top-k by inlier ratio, weighted mean / covariance
+//    (ransac_voting_gpu.py:318-329; _with_mean :392-402).  The k-th largest count is found with
+//    a 4-pass radix select over shared-memory histograms; among hypotheses tied at the k-th
+//    value the lowest indices are kept (torch.topk leaves this unspecified).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+distribution_kernel(epb_voting_params p, Workspace ws, const float* __restrict__ mean_in,
+                    float* __restrict__ mean_out, float* __restrict__ cov_out) {
+  const int v = blockIdx.x, b = blockIdx.y;
+  const int HN = p.hn * p.rounds;
+  float* mo = mean_out + ((size_t)b * p.vn + v) * 2;
+  float* co = cov_out + ((size_t)b * p.vn + v) * 4;
+  const bool with_mean = p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN;
+  if (!ws.live[b]) {
+    // hypotheses 0, ratios 1 (:273-278): mean 0 (or the given mean), cov = mean mean^T * sum/(sum[+1e-3])
+    if (threadIdx.x == 0) {
+      if (with_mean) {
+        const double mx = mean_in[((size_t)b * p.vn + v) * 2], my = mean_in[((size_t)b * p.vn + v) * 2 + 1];
+        const double s = (double)HN, den = s + 1e-3;
+        mo[0] = (float)mx; mo[1] = (float)my;
+        co[0] = (float)(mx * mx * s / den); co[1] = co[2] = (float)(mx * my * s / den);
+        co[3] = (float)(my * my * s / den);
+      } else {
+        mo[0] = mo[1] = 0.f; co[0] = co[1] = co[2] = co[3] = 0.f;
+      }
+    }
+    return;
+  }
+  __shared__ int hist[256];
+  __shared__ int s_sel[3];
+  __shared__ double s_red[6 * 8];
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  const int32_t* cnt = ws.counts + ((size_t)b * p.vn + v) * HN;
+  const float2* hyp = ws.hyp + ((size_t)b * p.vn + v) * HN;
+  const float tnf = (float)ws.tn[b];
+
+  unsigned thr_val = 0;  // k-th largest count
+  int need_eq = 0;       // how many of the ties at thr_val to keep
+  float ratio_floor = 0.f;
+  if (!with_mean) {
+    const int k = min(p.topk, HN);
+    unsigned prefix = 0, prefix_mask = 0;
+    int remaining = k;
+    for (int pass = 3; pass >= 0; --pass) {
+      hist[threadIdx.x] = 0;
+      __syncthreads();
+      const int shift = pass * 8;
+      for (int h = threadIdx.x; h < HN; h += 256) {
+        const unsigned c = (unsigned)cnt[h];
+        if ((c & prefix_mask) == prefix) atomicAdd(&hist[(c >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int acc = 0, bin = 255;
+        for (; bin > 0; --bin) {
+          if (acc + hist[bin] >= remaining) break;
+          acc += hist[bin];
+        }
+        s_sel[0] = bin; s_sel[1] = remaining - acc;
+      }
+      __syncthreads();
+      prefix |= (unsigned)s_sel[0] << shift;
+      prefix_mask |= 255u << shift;
+      remaining = s_sel[1];
+      __syncthreads();
+    }
+    thr_val = prefix;
+    need_eq = remaining;
+  } else {
+    int mx = 0;
+    for (int h = threadIdx.x; h < HN; h += 256) mx = max(mx, cnt[h]);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, m));
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    for (int w = 0; w < 8; ++w) mx = max(mx, s_warp[w]);
+    __syncthreads();
+    ratio_floor = __fsub_rn(__fdiv_rn((float)mx, tnf), 0.1f);  // max - 0.1 (:394)
+  }
+
+  // weights: pass A accumulates sum w, sum w*h; ordered so ties keep the lowest indices
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  double acc[6] = {0, 0, 0, 0, 0, 0};  // sw, swx, swy, sxx, sxy, syy
+  double mx_ = 0, my_ = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1) {
+      block_sum_d<6>(acc, s_red);
+      if (with_mean) {
+        mx_ = mean_in[((size_t)b * p.vn + v) * 2]; my_ = mean_in[((size_t)b * p.vn + v) * 2 + 1];
+      } else {
+        mx_ = acc[1] / acc[0]; my_ = acc[2] / acc[0];
+      }
+      if (threadIdx.x == 0) s_carry = 0;
+      __syncthreads();
+    }
+    for (int base = 0; base < HN; base += 256) {
+      const int h = base + threadIdx.x;
+      const bool valid = h < HN;
+      const unsigned c = valid ? (unsigned)cnt[h] : 0u;
+      float w = 0.f;
+      if (with_mean) {  // block-uniform branch
+        if (valid) {
+          const float r = __fdiv_rn((float)c, tnf);
+          w = (r < ratio_floor) ? 0.f : r;
+        }
+      } else {
+        const bool eq = valid && c == thr_val;
+        // rank among ties, in index order (all threads take every barrier)
+        const unsigned bal = __ballot_sync(FULL, eq);
+        const int before_in_warp = __popc(bal & ((1u << (threadIdx.x & 31)) - 1));
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        int before = s_carry + before_in_warp;
+        for (int wv = 0; wv < (int)(threadIdx.x >> 5); ++wv) before += s_warp[wv];
+        const bool keep = valid && (c > thr_val || (eq && before < need_eq));
+        w = keep ? __fdiv_rn((float)c, tnf) : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int wv = 0; wv < 8; ++wv) t += s_warp[wv]; s_carry += t; }
+        __syncthreads();
+      }
+      if (w != 0.f) {
+        const float2 q = hyp[h];
+        if (phase == 0) { acc[0] += w; acc[1] += (double)w * q.x; acc[2] += (double)w * q.y; }
+        else {
+          const double ddx = q.x - mx_, ddy = q.y - my_;
+          acc[3] += w * ddx * ddx; acc[4] += w * ddx * ddy; acc[5] += w * ddy * ddy;
+        }
+      }
+    }
+  }
+  const double sw = acc[0];  // reduced in phase switch
+  double c2[3] = {acc[3], acc[4], acc[5]};
+  block_sum_d<3>(c2, s_red);
+  if (threadIdx.x == 0) {
+    const double den = with_mean ? sw + 1e-3 : sw;
+    mo[0] = (float)mx_; mo[1] = (float)my_;
+    co[0] = (float)(c2[0] / den); co[1] = co[2] = (float)(c2[1] / den); co[3] = (float)(c2[2] / den);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pybind-level primitives (reference tensor layouts)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+generate_hypothesis_kernel(const float* __restrict__ direct, const float* __restrict__ coords,
+                           const int32_t* __restrict__ idxs, float* __restrict__ hypo, int tn, int vn,
+                           int hn) {
+  const int hvi = blockIdx.x * 256 + threadIdx.x;
+  if (hvi >= hn * vn) return;
+  const int vi = hvi % vn;
+  const int t0 = idxs[hvi * 2], t1 = idxs[hvi * 2 + 1];
+  float x = 0.f, y = 0.f, ix, iy;
+  if (intersect_rays(direct[(size_t)t0 * vn * 2 + vi * 2], direct[(size_t)t0 * vn * 2 + vi * 2 + 1],
+                     coords[t0 * 2], coords[t0 * 2 + 1], direct[(size_t)t1 * vn * 2 + vi * 2],
+                     direct[(size_t)t1 * vn * 2 + vi * 2 + 1], coords[t1 * 2], coords[t1 * 2 + 1], &ix, &iy)) {
+    x = ix; y = iy;
+  }
+  hypo[hvi * 2] = x;
+  hypo[hvi * 2 + 1] = y;
+}
+
+__global__ void __launch_bounds__(256)
+voting_for_hypothesis_kernel(const float* __restrict__ direct, const float* __restrict__ coords,
+                             const float* __restrict__ hypo, uint8_t* __restrict__ inliers, int tn,
+                             int vn, int hn, float thresh) {
+  const int ti = blockIdx.x * 256 + threadIdx.x;
+  const int hv = blockIdx.y;  // hi*vn + vi
+  if (ti >= tn) return;
+  const int vi = hv % vn;
+  const float nx = direct[(size_t)ti * vn * 2 + vi * 2], ny = direct[(size_t)ti * vn * 2 + vi * 2 + 1];
+  if (vote_exact(coords[ti * 2], coords[ti * 2 + 1], nx, ny, dir_norm(nx, ny), hypo[hv * 2],
+                 hypo[hv * 2 + 1], thresh))
+    inliers[(size_t)hv * tn + ti] = 1;
+}
+
+// ransac_voting_kernel.cu:170-229.  Plain float arithmetic in source order (no claim of
+// bit-exactness against the reference build for this variant).
+__global__ void __launch_bounds__(256)
+generate_hypothesis_vp_kernel(const float* __restrict__ direct, const float* __restrict__ coords,
+                              const int32_t* __restrict__ idxs, float* __restrict__ hypo, int tn,
+                              int vn, int hn) {
+  const int hvi = blockIdx.x * 256 + threadIdx.x;
+  if (hvi >= hn * vn) return;
+  const int vi = hvi % vn;
+  const int id0 = idxs[hvi * 2], id1 = idxs[hvi * 2 + 1];
+  const float dx0 = direct[(size_t)id0 * vn * 2 + vi * 2], dy0 = direct[(size_t)id0 * vn * 2 + vi * 2 + 1];
+  const float cx0 = coords[id0 * 2], cy0 = coords[id0 * 2 + 1];
+  const float dx1 = direct[(size_t)id1 * vn * 2 + vi * 2], dy1 = direct[(size_t)id1 * vn * 2 + vi * 2 + 1];
+  const float cx1 = coords[id1 * 2], cy1 = coords[id1 * 2 + 1];
+  const float lx0 = dy0, ly0 = -dx0, lz0 = cy0 * dx0 - cx0 * dy0;
+  const float lx1 = dy1, ly1 = -dx1, lz1 = cy1 * dx1 - cx1 * dy1;
+  float x = ly0 * lz1 - lz0 * ly1;
+  float y = lz0 * lx1 - lx0 * lz1;
+  float z = lx0 * ly1 - ly0 * lx1;
+  const float val_x0 = dx0 * (x - z * cx0), val_x1 = dx1 * (x - z * cx1);
+  const float val_y0 = dy0 * (y - z * cy0), val_y1 = dy1 * (y - z * cy1);
+  if (val_x0 < 0 && val_x1 < 0 && val_y0 < 0 && val_y1 < 0) { z = -z; x = -x; y = -y; }
+  if (val_x0 * val_x1 < 0 || val_y0 * val_y1 < 0) { x = 0.f; y = 0.f; z = 0.f; }
+  hypo[hvi * 3] = x; hypo[hvi * 3 + 1] = y; hypo[hvi * 3 + 2] = z;
+}
+
+// ransac_voting_kernel.cu:268-310
+__global__ void __launch_bounds__(256)
+voting_for_hypothesis_vp_kernel(const float* __restrict__ direct, const float* __restrict__ coords,
+                                const float* __restrict__ hypo, uint8_t* __restrict__ inliers, int tn,
+                                int vn, int hn, float thresh) {
+  const int ti = blockIdx.x * 256 + threadIdx.x;
+  const int hv = blockIdx.y;
+  if (ti >= tn) return;
+  const int vi = hv % vn;
+  const float cx = coords[ti * 2], cy = coords[ti * 2 + 1];
+  const float hx = hypo[hv * 3], hy = hypo[hv * 3 + 1], hz = hypo[hv * 3 + 2];
+  const float ddx = direct[(size_t)ti * vn * 2 + vi * 2], ddy = direct[(size_t)ti * vn * 2 + vi * 2 + 1];
+  const float fx = hx - cx * hz, fy = hy - cy * hz;
+  const float norm1 = __fsqrt_rn(ddx * ddx + ddy * ddy);
+  const float norm2 = __fsqrt_rn(fx * fx + fy * fy);
+  if ((double)norm1 < 1e-6 || (double)norm2 < 1e-6) return;
+  const float ad = __fdiv_rn(ddx * fx + ddy * fy, norm1 * norm2);
+  const float vx = fx * ddx, vy = fy * ddy;
+  if (vx < 0 || vy < 0) return;
+  if (fabsf(ad) > thresh) inliers[(size_t)hv * tn + ti] = 1;
+}
+
+}  // namespace epb
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using namespace epb;
+
+static bool params_ok(const epb_voting_params* p) {
+  if (!p) return false;
+  if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->vn <= 0 || p->hn <= 0 || p->rounds <= 0) return false;
+  if (p->H > 65535 || p->W > 65535) return false;
+  if ((long long)p->H * p->W > 0x7fffffffLL) return false;
+  if (p->mode < EPB_VOTE_V3 || p->mode > EPB_VOTE_DISTRIBUTION_WITH_MEAN) return false;
+  if (p->rng_mode < EPB_RNG_IDXS || p->rng_mode > EPB_RNG_PHILOX) return false;
+  if ((long long)p->hn * p->rounds > (1 << 24)) return false;
+  return true;
+}
+
+extern "C" size_t epb_voting_workspace_bytes(const epb_voting_params* p) {
+  if (!params_ok(p)) return 0;
+  return carve(*p, nullptr).bytes;
+}
+
+extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* io, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (!params_ok(pp) || !io || !io->mask || !io->vertex || !workspace) return EPB_ERR_INVALID;
+  const epb_voting_params p = *pp;
+  if (p.rng_mode != EPB_RNG_PHILOX && !io->idxs) return EPB_ERR_INVALID;
+  const bool is_layer = p.mode <= EPB_VOTE_V5;
+  const bool is_dist = p.mode >= EPB_VOTE_DISTRIBUTION;
+  if (is_layer && !io->pts) return EPB_ERR_INVALID;
+  if ((p.mode == EPB_VOTE_V4 || p.mode == EPB_VOTE_V5) && !io->var_or_conf) return EPB_ERR_INVALID;
+  if (p.mode == EPB_VOTE_HYPOTHESIS && (!io->hyp || !io->counts)) return EPB_ERR_INVALID;
+  if (is_dist && (!io->mean || !io->cov)) return EPB_ERR_INVALID;
+  if (p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN && !io->mean_in) return EPB_ERR_INVALID;
+  if (is_dist && p.topk <= 0 && p.mode == EPB_VOTE_DISTRIBUTION) return EPB_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return EPB_ERR_INVALID;
+  Workspace ws = carve(p, workspace);
+  if (workspace_bytes < ws.bytes) return EPB_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  const int HW = p.H * p.W;
+  const int T = (HW + TILE_PX - 1) / TILE_PX;
+  const int HN = p.hn * p.rounds;
+  const TorchRngLayout lu = torch_rng_layout((unsigned long long)HW, p.philox_sm_count, p.philox_threads_per_sm);
+  const TorchRngLayout lr = torch_rng_layout((unsigned long long)p.hn * p.vn * 2, p.philox_sm_count,
+                                             p.philox_threads_per_sm);
+  SubsampleCtx sc;
+  sc.selection = io->selection;
+  sc.seed = p.philox_seed;
+  sc.total_threads = lu.total_threads;
+  sc.use_philox = (p.rng_mode == EPB_RNG_PHILOX) && !io->selection;
+  // the subsample can only trigger when an image can hold more than max_num foreground pixels
+  const int allow_sub = (HW > p.max_num) && (io->selection || sc.use_philox);
+
+  mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 0, ws, sc);
+  EPB_RETURN_IF(check_launch());
+  mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 0, p.min_num, p.max_num, allow_sub, ws);
+  EPB_RETURN_IF(check_launch());
+  rng_offsets_kernel<<<1, 32, 0, s>>>(p.B, p.rounds, p.philox_offset, lu.inc, lr.inc, ws,
+                                      io->philox_consumed, nullptr);
+  EPB_RETURN_IF(check_launch());
+  if (allow_sub) {
+    mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 1, ws, sc);
+    EPB_RETURN_IF(check_launch());
+    mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 1, p.min_num, p.max_num, allow_sub, ws);
+    EPB_RETURN_IF(check_launch());
+  }
+  mask_scatter_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc);
+  EPB_RETURN_IF(check_launch());
+  if (io->tn_out)
+    EPB_RETURN_IF(check_api(cudaMemcpyAsync(io->tn_out, ws.tn, (size_t)p.B * 4, cudaMemcpyDeviceToDevice, s)));
+
+  HypCtx hc;
+  hc.idxs = io->idxs;
+  hc.rng_mode = p.rng_mode;
+  hc.seed = p.philox_seed;
+  hc.total_threads_r = lr.total_threads;
+  hc.inc_r = lr.inc;
+  {
+    const long long n = (long long)p.B * HN * p.vn;
+    hypothesis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(io->vertex, p, ws, hc, io->hyp);
+    EPB_RETURN_IF(check_launch());
+  }
+  {
+    // R hypotheses per thread; split the pixels of an image over several CTAs when the batch
+    // alone cannot fill the 148 SMs (>= 2 waves of 128-thread CTAs at 16 CTAs/SM is plenty).
+    const int R = HN <= 128 ? 1 : HN <= 256 ? 2 : 4;
+    const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
+    const long long ctas = (long long)p.B * p.vn * chunks;
+    int splits = 1;
+    const long long target = 148LL * 8;
+    if (ctas < target) {
+      splits = (int)((target + ctas - 1) / ctas);
+      const int max_splits = (HW + 4 * VOTE_TILE - 1) / (4 * VOTE_TILE);
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+    const int use_atomic = splits > 1;
+    if (use_atomic)
+      EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
+    dim3 grid(splits, p.vn * chunks, p.B);
+    if (R == 1) vote_count_kernel<1><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
+    else if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
+    else vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
+    EPB_RETURN_IF(check_launch());
+  }
+  if (io->counts) {
+    const long long n = (long long)p.B * HN * p.vn;
+    counts_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, ws, io->counts);
+    EPB_RETURN_IF(check_launch());
+  }
+  if (is_layer) {
+    winner_refine_kernel<<<dim3(p.vn, p.B), 256, 0, s>>>(io->vertex, p, ws, io->pts, io->var_or_conf,
+                                                         io->status);
+    EPB_RETURN_IF(check_launch());
+  } else if (is_dist) {
+    distribution_kernel<<<dim3(p.vn, p.B), 256, 0, s>>>(p, ws, io->mean_in, io->mean, io->cov);
+    EPB_RETURN_IF(check_launch());
+  }
+  return EPB_OK;
+}
+
+extern "C" int epb_generate_hypothesis(const float* direct, const float* coords, const int32_t* idxs,
+                                       float* hypo, int tn, int vn, int hn, void* stream) {
+  if (!direct || !coords || !idxs || !hypo || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
+  generate_hypothesis_kernel<<<(hn * vn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(direct, coords, idxs,
+                                                                                  hypo, tn, vn, hn);
+  return check_launch();
+}
+
+extern "C" int epb_voting_for_hypothesis(const float* direct, const float* coords, const float* hypo,
+                                         uint8_t* inliers, int tn, int vn, int hn, float thresh,
+                                         void* stream) {
+  if (!direct || !coords || !hypo || !inliers || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
+  if ((long long)hn * vn > 65535) {
+    // grid.y limit: process in slabs of hypotheses
+    const int per = 65535 / vn;
+    for (int h0 = 0; h0 < hn; h0 += per) {
+      const int n = hn - h0 < per ? hn - h0 : per;
+      voting_for_hypothesis_kernel<<<dim3((tn + 255) / 256, n * vn), 256, 0, (cudaStream_t)stream>>>(
+          direct, coords, hypo + (size_t)h0 * vn * 2, inliers + (size_t)h0 * vn * tn, tn, vn, n, thresh);
+      EPB_RETURN_IF(check_launch());
+    }
+    return EPB_OK;
+  }
+  voting_for_hypothesis_kernel<<<dim3((tn + 255) / 256, hn * vn), 256, 0, (cudaStream_t)stream>>>(
+      direct, coords, hypo, inliers, tn, vn, hn, thresh);
+  return check_launch();
+}
+
+extern "C" int epb_generate_hypothesis_vanishing_point(const float* direct, const float* coords,
+                                                       const int32_t* idxs, float* hypo3, int tn, int vn,
+                                                       int hn, void* stream) {
+  if (!direct || !coords || !idxs || !hypo3 || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
+  generate_hypothesis_vp_kernel<<<(hn * vn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      direct, coords, idxs, hypo3, tn, vn, hn);
+  return check_launch();
+}
+
+extern "C" int epb_voting_for_hypothesis_vanishing_point(const float* direct, const float* coords,
+                                                         const float* hypo3, uint8_t* inliers, int tn,
+                                                         int vn, int hn, float thresh, void* stream) {
+  if (!direct || !coords || !hypo3 || !inliers || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
+  if ((long long)hn * vn > 65535) return EPB_ERR_INVALID;
+  voting_for_hypothesis_vp_kernel<<<dim3((tn + 255) / 256, hn * vn), 256, 0, (cudaStream_t)stream>>>(
+      direct, coords, hypo3, inliers, tn, vn, hn, thresh);
+  return check_launch();
+}

@@ -1,0 +1,183 @@
+"""PnP initialisation and LM refinement -- drop-ins for the reference's ``pnp.py``, the ``cpnp``
+extension and ``lib/utils/extend_utils`` ``uncertainty_pnp`` on the CUDA path.
+
+  pnp(points_3d, points_2d, camera_matrix, method)      /root/reference/pnp.py:46-90
+  cpnp(p3d, p2d, K, camera) / cpnp_m(p3d, p2d, maxvals, K, camera)   val.py:200-202
+  uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix)   extend_utils.py:64-115
+and the batched, device-resident forms ``pnp_batch`` / ``lm_refine_batch`` / ``pose_pipeline``
+that the B200 path is built for.  All arithmetic is csrc/pose.cu (one warp per image, FP64).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+# cv2 constants (cv2 is not imported on the product path)
+SOLVEPNP_ITERATIVE = 0
+SOLVEPNP_EPNP = 1
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("esa_pose_estimation_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _f64(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(device=device, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(device)
+
+
+# ------------------------------------------------------------------------------------ batched
+def pnp_batch(p3d, p2d, K, npts=None, reproj_err=5.0, max_iters=100, confidence=0.99,
+              return_status=False):
+    """p3d [B,n,3] or [n,3] (shared model), p2d [B,n,2], K [B,3,3] or [3,3]; CUDA float64.
+    -> rt34 [B,3,4] float64 ([R|t]); with return_status also (inlier_mask [B] int64, status [B])."""
+    dev = p2d.device if isinstance(p2d, torch.Tensor) and p2d.is_cuda else _device()
+    p3d, p2d, K = _f64(p3d, dev), _f64(p2d, dev), _f64(K, dev)
+    b, n = p2d.shape[0], p2d.shape[1]
+    rt = torch.empty((b, 3, 4), dtype=torch.float64, device=dev)
+    mask = torch.zeros((b,), dtype=torch.int64, device=dev)
+    status = torch.zeros((b,), dtype=torch.int32, device=dev)
+    if npts is not None:
+        npts = npts.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        st = _lib.load().epb_pnp_epnp_ransac(
+            _lib.ptr(p3d), int(p3d.dim() == 3), _lib.ptr(p2d), _lib.ptr(K), int(K.dim() == 3),
+            _lib.ptr(npts), b, n, float(reproj_err), int(max_iters), float(confidence), _lib.ptr(rt),
+            _lib.ptr(mask), _lib.ptr(status), _lib.stream_ptr())
+    _lib.check(st, "epb_pnp_epnp_ransac")
+    return (rt, mask, status) if return_status else rt
+
+
+def lm_refine_batch(p2d, p3d, w2d, K, init_rt, npts=None, return_info=False):
+    """Batched uncertainty_pnp: p2d [B,n,2], p3d [B,n,3] | [n,3], w2d [B,n,3] (wxx,wxy,wyy),
+    K [B,3,3] | [3,3], init_rt [B,6] -> rt [B,6] (angle-axis, t), CUDA float64."""
+    dev = p2d.device if isinstance(p2d, torch.Tensor) and p2d.is_cuda else _device()
+    p2d, p3d, w2d, K, init_rt = (_f64(a, dev) for a in (p2d, p3d, w2d, K, init_rt))
+    b, n = p2d.shape[0], p2d.shape[1]
+    out = torch.empty((b, 6), dtype=torch.float64, device=dev)
+    iters = torch.zeros((b,), dtype=torch.int32, device=dev)
+    cost = torch.zeros((b,), dtype=torch.float64, device=dev)
+    if npts is not None:
+        npts = npts.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        st = _lib.load().epb_lm_refine(_lib.ptr(p2d), _lib.ptr(p3d), int(p3d.dim() == 3), _lib.ptr(w2d),
+                                       _lib.ptr(K), int(K.dim() == 3), _lib.ptr(init_rt), _lib.ptr(npts), b, n,
+                                       _lib.ptr(out), _lib.ptr(iters), _lib.ptr(cost), _lib.stream_ptr())
+    _lib.check(st, "epb_lm_refine")
+    return (out, iters, cost) if return_info else out
+
+
+def rt34_to_rt6(rt34):
+    """[B,3,4] -> [B,6] (cv2.Rodrigues matrix -> vector, then t)."""
+    rt34 = rt34.contiguous()
+    out = torch.empty((rt34.shape[0], 6), dtype=torch.float64, device=rt34.device)
+    with torch.cuda.device(rt34.device):
+        _lib.check(_lib.load().epb_rt34_to_rt6(_lib.ptr(rt34), rt34.shape[0], _lib.ptr(out), _lib.stream_ptr()),
+                   "epb_rt34_to_rt6")
+    return out
+
+
+def pose_pack(rt6):
+    """[B,6] -> (pose7 [B,7] f32 = (qw,qx,qy,qz,tx,ty,tz), rt34 [B,3,4] f64)  (val.py:203-224)."""
+    rt6 = rt6.contiguous()
+    b = rt6.shape[0]
+    pose7 = torch.empty((b, 7), dtype=torch.float32, device=rt6.device)
+    rt34 = torch.empty((b, 3, 4), dtype=torch.float64, device=rt6.device)
+    with torch.cuda.device(rt6.device):
+        _lib.check(_lib.load().epb_pose_pack(_lib.ptr(rt6), b, _lib.ptr(pose7), _lib.ptr(rt34), _lib.stream_ptr()),
+                   "epb_pose_pack")
+    return pose7, rt34
+
+
+def pose_pipeline(preds, maxvals, bbox_xy, rate, p3d_model, K, min_k=24, sel_thresh=0.8, weighted=True):
+    """val.py:172-228 for a batch, one stream-ordered call.
+    preds [B,Kp,2] f32 (crop px), maxvals [B,Kp] f32, bbox_xy [B,2], rate [B], p3d_model [Kp,3], K [3,3].
+    -> dict(pose7 [B,7] f32, rt6 [B,6] f64, epnp_rt34 [B,3,4] f64, status [B] i32)."""
+    dev = preds.device
+    preds = preds.to(torch.float32).contiguous()
+    maxvals = maxvals.to(torch.float32).contiguous()
+    bbox_xy, rate, p3d_model, K = _f64(bbox_xy, dev), _f64(rate, dev), _f64(p3d_model, dev), _f64(K, dev)
+    b, kp = preds.shape[0], preds.shape[1]
+    pose7 = torch.empty((b, 7), dtype=torch.float32, device=dev)
+    rt6 = torch.empty((b, 6), dtype=torch.float64, device=dev)
+    epnp = torch.empty((b, 3, 4), dtype=torch.float64, device=dev)
+    status = torch.zeros((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.load().epb_pose_pipeline(_lib.ptr(preds), _lib.ptr(maxvals), _lib.ptr(bbox_xy), _lib.ptr(rate),
+                                           _lib.ptr(p3d_model), _lib.ptr(K), b, kp, int(min_k), float(sel_thresh),
+                                           int(bool(weighted)), _lib.ptr(pose7), _lib.ptr(rt6), _lib.ptr(epnp),
+                                           _lib.ptr(status), _lib.stream_ptr())
+    _lib.check(st, "epb_pose_pipeline")
+    return dict(pose7=pose7, rt6=rt6, epnp_rt34=epnp, status=status)
+
+
+def esa_score(pose7_pred, pose7_gt):
+    """demo.py:295-310 -> (score_t [B], score_r [B]) float64 on the device."""
+    pred = pose7_pred.to(torch.float32).contiguous()
+    gt = pose7_gt.to(device=pred.device, dtype=torch.float32).contiguous()
+    b = pred.shape[0]
+    st_ = torch.empty((b,), dtype=torch.float64, device=pred.device)
+    sr_ = torch.empty((b,), dtype=torch.float64, device=pred.device)
+    with torch.cuda.device(pred.device):
+        _lib.check(_lib.load().epb_esa_score(_lib.ptr(pred), _lib.ptr(gt), b, _lib.ptr(st_), _lib.ptr(sr_),
+                                             _lib.stream_ptr()), "epb_esa_score")
+    return st_, sr_
+
+
+# ------------------------------------------------------------------------------------ drop-ins
+def pnp(points_3d, points_2d, camera_matrix, method=SOLVEPNP_ITERATIVE):
+    """pnp.py:46-90: RANSAC-EPnP (reprojectionError 5 px) -> [3,4] float64 [R|t].
+    As in the reference the solver does not depend on `method` and a failed RANSAC is not
+    reported (cv2 leaves stale memory there; this returns NaN)."""
+    assert points_3d.shape[0] == points_2d.shape[0], 'points 3D and points 2D must have same number of vertices'
+    dev = _device()
+    rt = pnp_batch(_f64(points_3d, dev)[None], _f64(points_2d, dev)[None], _f64(camera_matrix, dev))
+    return rt[0].cpu().numpy()
+
+
+def _flat_k(K):
+    k = K.detach().cpu().numpy() if isinstance(K, torch.Tensor) else np.asarray(K)
+    return np.asarray(k, np.float64).reshape(-1)[-9:].reshape(3, 3)   # accepts the batched [1,3,3] of val.py:140
+
+
+def cpnp(p3d, p2d, K, camera):
+    """cpnp.cpnp(p3d, p2d, K, camera[6]) -> camera[6] (val.py:200): unit-weight LM refinement."""
+    n = np.asarray(p3d).shape[0]
+    w = np.stack([np.ones(n), np.zeros(n), np.ones(n)], 1)
+    dev = _device()
+    out = lm_refine_batch(_f64(p2d, dev)[None], _f64(p3d, dev)[None], _f64(w, dev)[None], _f64(_flat_k(K), dev),
+                          _f64(camera, dev).reshape(1, 6))
+    return out[0].cpu().numpy()
+
+
+def cpnp_m(p3d, p2d, maxvals, K, camera):
+    """cpnp.cpnp_m(p3d, p2d, maxvals, K, camera[6]) -> camera[6] (val.py:202): LM refinement weighted
+    by the heatmap maxima (wxx = wyy = maxval, wxy = 0 -- the cpnp source is absent from the
+    reference, so this weighting is an assumption)."""
+    mv = np.asarray(maxvals, np.float64).reshape(-1)
+    w = np.stack([mv, np.zeros_like(mv), mv], 1)
+    dev = _device()
+    out = lm_refine_batch(_f64(p2d, dev)[None], _f64(p3d, dev)[None], _f64(w, dev)[None], _f64(_flat_k(K), dev),
+                          _f64(camera, dev).reshape(1, 6))
+    return out[0].cpu().numpy()
+
+
+def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix, init_rt=None):
+    """extend_utils.py:64-115 -> [3,4].  The reference initialises with cv2's P3P on the four
+    best-weighted points; here the initial pose is RANSAC-EPnP on all points unless `init_rt`
+    ([6] angle-axis, t) is given.  Both converge to the same LM minimiser on well-posed input."""
+    pn = points_2d.shape[0]
+    assert points_3d.shape[0] == pn and pn >= 4
+    dev = _device()
+    p2, p3, w = _f64(points_2d, dev)[None], _f64(points_3d, dev)[None], _f64(weights_2d, dev)[None]
+    K = _f64(camera_matrix, dev)
+    if init_rt is None:
+        init = rt34_to_rt6(pnp_batch(p3, p2, K))
+    else:
+        init = _f64(init_rt, dev).reshape(1, 6)
+    rt6 = lm_refine_batch(p2, p3, w, K, init)
+    _, rt34 = pose_pack(rt6)
+    return rt34[0].cpu().numpy()

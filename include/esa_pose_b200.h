@@ -1,0 +1,195 @@
+/* esa_pose_b200.h -- C ABI of the B200-native post-network pose hot path.
+ *
+ * Drop-in boundary for bonjour-l/esa-pose-estimation.  Every entry
+ * point takes plain DEVICE pointers and sizes plus a CUDA stream (cudaStream_t passed as
+ * void*), never allocates, never synchronises the host, and returns an int status
+ * (EPB_OK == 0) instead of the reference's exit()-on-error (cuda_common.h:17-26).
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *
+ *   epb_decode_heatmaps              inference.py:22 get_max_preds, :136 get_final (+ :75 my_taylor),
+ *                                    :171 getPrediction; val.py:151-164 two-stage torch.max
+ *   epb_generate_hypothesis          lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:20
+ *                                    (pybind ransac_voting.generate_hypothesis -> kernel .cu:11)
+ *   epb_voting_for_hypothesis        ransac_voting.cpp:41 (-> kernel .cu:88)
+ *   epb_generate_hypothesis_vanishing_point / epb_voting_for_hypothesis_vanishing_point
+ *                                    ransac_voting.cpp:64,85 (-> kernels .cu:170,268)
+ *   epb_voting_workspace_bytes, epb_voting_run
+ *                                    ransac_voting_gpu.py:514 ransac_voting_layer_v3, :669 _v4,
+ *                                    :763 _v5, :218 ransac_voting_hypothesis,
+ *                                    :263 estimate_voting_distribution, :333 ..._with_mean
+ *                                    (whole Python driver, batched, one stream-ordered call)
+ *   epb_pnp_epnp_ransac              pnp.py:46 pnp() == cv2.solvePnPRansac(EPNP, 5 px) + Rodrigues
+ *   epb_lm_refine                    lib/utils/extend_utils/src/utils_python_binding.h:23-31
+ *                                    uncertainty_pnp(); val.py:200-202 cpnp.cpnp / cpnp.cpnp_m
+ *   epb_pose_pack                    val.py:203-224 Rodrigues + scipy as_quat -> (w,x,y,z), t
+ *   epb_pose_pipeline                val.py:172-228 per-frame glue, batched (select, un-crop,
+ *                                    EPnP-RANSAC, LM, quaternion)
+ *   epb_esa_score                    demo.py:295-310
+ */
+#ifndef ESA_POSE_B200_H_
+#define ESA_POSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPB_VERSION 100
+
+enum {
+  EPB_OK = 0,
+  EPB_ERR_INVALID = 1,    /* bad argument (null pointer, non-positive size, unsupported mode) */
+  EPB_ERR_CUDA = 2,       /* a CUDA launch failed; see epb_last_cuda_error() */
+  EPB_ERR_WORKSPACE = 3,  /* workspace smaller than epb_*_workspace_bytes() */
+  EPB_ERR_NO_DEVICE = 4
+};
+
+int epb_version(void);
+/* CUDA error code of the last failing launch on this thread (0 if none) and its string. */
+int epb_last_cuda_error(void);
+const char* epb_last_cuda_error_string(void);
+/* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
+unsigned long long epb_launch_count(void);
+/* SM count / clock of the current device (roofline reporting). */
+int epb_device_info(int* sm_count, int* sm_clock_khz, size_t* l2_bytes);
+
+/* ------------------------------------------------------------------ heatmap decode (a1,a2) */
+enum {
+  EPB_DECODE_REFINE = 1,        /* log-domain sub-pixel step of inference.py:75-94 */
+  EPB_DECODE_ZERO_NONPOS = 2    /* zero the coordinates when maxval <= 0 (inference.py:183-184) */
+};
+/* hm [n_maps,H,W] f32 contiguous (n_maps = B*K).  xy [n_maps,2] f32 (x = column, y = row),
+ * maxval [n_maps] f32, idx [n_maps] i32 (flat row-major argmax; first maximum; NaN counts as
+ * the maximum, like torch.max / np.argmax).  Any output pointer may be NULL. */
+int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, int flags, float* xy,
+                        float* maxval, int32_t* idx, void* stream);
+
+/* inference.py:136 get_final on caller-supplied peaks: xy [n_maps,2] f32 in/out (the integer part
+ * of each coordinate selects the stencil centre, exactly like int(coord[0]) at inference.py:79). */
+int epb_refine_keypoints(const float* hm, int n_maps, int H, int W, float* xy, void* stream);
+
+/* ------------------------------------------------- pybind-level voting primitives (a9,a10,a21) */
+/* direct [tn,vn,2] f32, coords [tn,2] f32, idxs [hn,vn,2] i32 -> hypo [hn,vn,2] f32.
+ * Unlike the reference (which returns at::zeros and skips degenerate pairs) the kernel writes
+ * the zeros itself, so `hypo` need not be pre-zeroed. */
+int epb_generate_hypothesis(const float* direct, const float* coords, const int32_t* idxs,
+                            float* hypo, int tn, int vn, int hn, void* stream);
+/* Writes 1 where the pixel votes for the hypothesis; other bytes untouched (caller zeroes,
+ * ransac_voting_gpu.py:557).  inliers [hn,vn,tn] u8. */
+int epb_voting_for_hypothesis(const float* direct, const float* coords, const float* hypo,
+                              uint8_t* inliers, int tn, int vn, int hn, float thresh, void* stream);
+int epb_generate_hypothesis_vanishing_point(const float* direct, const float* coords,
+                                            const int32_t* idxs, float* hypo3, int tn, int vn,
+                                            int hn, void* stream);
+int epb_voting_for_hypothesis_vanishing_point(const float* direct, const float* coords,
+                                              const float* hypo3, uint8_t* inliers, int tn, int vn,
+                                              int hn, float thresh, void* stream);
+
+/* ------------------------------------------------------- fused batched voting (a6-a14) */
+enum {
+  EPB_VOTE_V3 = 0,           /* -> pts */
+  EPB_VOTE_V4 = 1,           /* -> pts, var */
+  EPB_VOTE_V5 = 2,           /* -> pts, conf (re-vote at 0.999) */
+  EPB_VOTE_HYPOTHESIS = 3,   /* -> hyp [B,hn,vn,2], counts [B,hn,vn] */
+  EPB_VOTE_DISTRIBUTION = 4, /* -> mean, cov (top-k) */
+  EPB_VOTE_DISTRIBUTION_WITH_MEAN = 5
+};
+enum {
+  EPB_MASK_NONZERO = 0, /* v3/v4/v5: mask.byte() != 0 */
+  EPB_MASK_EQ1 = 1      /* hypothesis / distribution: mask == 1 */
+};
+enum {
+  EPB_RNG_IDXS = 0,   /* hypothesis indices supplied: idxs [B,rounds,hn,vn,2] i32 (values < tn) */
+  EPB_RNG_RAW32 = 1,  /* raw 32-bit draws supplied in `idxs`; index = draw % tn on device */
+  EPB_RNG_PHILOX = 2  /* Philox4x32-10 in the layout of torch's CUDA random_() / uniform_() */
+};
+
+typedef struct {
+  int mode;             /* EPB_VOTE_* */
+  int B, H, W, vn;
+  int hn;               /* round_hyp_num */
+  int rounds;           /* 1 for v3/v4/v5/hypothesis; ceil(min_hyp_num/round_hyp_num) otherwise */
+  float inlier_thresh;
+  int min_num, max_num;
+  int topk;             /* distribution only */
+  int mask_mode;        /* EPB_MASK_* */
+  /* vertex element strides (in floats) so that both the physical NCHW output of the network,
+   * viewed as [b,h,w,vn,2] by vertex_layer_reshape (base_utils.py:311-316), and a contiguous
+   * [b,h,w,vn,2] tensor are consumed without a copy: element (b,y,x,v,c) is at
+   * vertex[b*sb + y*sy + x*sx + v*sv + c*sc]. */
+  long long sb, sy, sx, sv, sc;
+  int rng_mode;         /* EPB_RNG_* */
+  unsigned long long philox_seed;
+  unsigned long long philox_offset; /* torch generator offset before the call */
+  int philox_sm_count;  /* multiProcessorCount torch would see (grid clamp of its RNG kernels) */
+  int philox_threads_per_sm; /* maxThreadsPerMultiProcessor */
+} epb_voting_params;
+
+size_t epb_voting_workspace_bytes(const epb_voting_params* p);
+
+typedef struct {
+  const uint8_t* mask;      /* [B,H,W] u8 */
+  const float* vertex;      /* strided, see params */
+  const int32_t* idxs;      /* EPB_RNG_IDXS / RAW32: [B,rounds,hn,vn,2]; else NULL */
+  const float* selection;   /* optional [B,H,W] f32 uniform draws for the max_num subsample
+                               (EPB_RNG_IDXS / RAW32); NULL -> Philox or no subsample possible */
+  const float* mean_in;     /* DISTRIBUTION_WITH_MEAN: [B,vn,2] */
+  float* pts;               /* [B,vn,2]   v3/v4/v5 */
+  float* var_or_conf;       /* [B,vn]     v4 / v5 */
+  float* hyp;               /* [B,rounds*hn,vn,2]  HYPOTHESIS (optional otherwise) */
+  int32_t* counts;          /* [B,rounds*hn,vn]    HYPOTHESIS (optional otherwise) */
+  float* mean;              /* [B,vn,2]   DISTRIBUTION* */
+  float* cov;               /* [B,vn,2,2] DISTRIBUTION* */
+  int32_t* tn_out;          /* optional [B]: foreground count after the subsample */
+  int32_t* status;          /* optional [B,vn]: 0 ok, 1 image skipped (< min_num), 2 singular refine */
+  unsigned long long* philox_consumed; /* optional [1]: generator offset increment (EPB_RNG_PHILOX) */
+} epb_voting_io;
+
+int epb_voting_run(const epb_voting_params* p, const epb_voting_io* io, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ pose (a15-a19) */
+/* All pose entry points are batched, one warp per image, FP64.
+ * p3d [B,n_max,3] (or [n_max,3] if p3d_batched == 0), p2d [B,n_max,2], K [B,9] or [9] row-major
+ * (fx=K[0], fy=K[4], cx=K[2], cy=K[5]), npts [B] (NULL -> all n_max).  n_max <= 32 (one lane per
+ * correspondence; the reference uses 11..30 keypoints), else EPB_ERR_INVALID. */
+enum {
+  EPB_POSE_OK = 0,
+  EPB_POSE_FAILED = 1,      /* no consensus (cv2 returns ok=False and stale memory; we return NaN) */
+  EPB_POSE_TOO_FEW = 2
+};
+/* pnp.pnp(): rt34 [B,3,4] f64 row-major [R|t]; inlier_mask [B] u64 bitmask (optional);
+ * status [B] (optional). */
+int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const double* p2d, const double* K,
+                        int K_batched, const int32_t* npts, int B, int n_max,
+                        double reproj_err, int max_iters, double confidence, double* rt34,
+                        unsigned long long* inlier_mask, int32_t* status, void* stream);
+/* uncertainty_pnp C entry, batched: w2d [B,n_max,3] = (wxx,wxy,wyy); init_rt/result_rt [B,6]
+ * (angle-axis, t).  iters/final_cost optional. */
+int epb_lm_refine(const double* p2d, const double* p3d, int p3d_batched, const double* w2d,
+                  const double* K, int K_batched, const double* init_rt, const int32_t* npts, int B,
+                  int n_max, double* result_rt, int32_t* iters, double* final_cost, void* stream);
+/* rt6 [B,6] -> pose7 [B,7] f32 (qw,qx,qy,qz,tx,ty,tz) and rt34 [B,3,4] f64 (either optional). */
+int epb_pose_pack(const double* rt6, int B, float* pose7, double* rt34, void* stream);
+/* R [B,3,3] (inside rt34 [B,3,4]) -> angle-axis like cv2.Rodrigues; rt6 [B,6]. */
+int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* stream);
+
+/* val.py:172-228 batched.  preds [B,K,2] f32 crop px, maxvals [B,K] f32, bbox_xy [B,2] f64,
+ * rate [B] f64, p3d_model [K,3] f64 (shared) , Kmat [9] f64.
+ * Selects large_k = max(#(maxval > sel_thresh), min_k) best keypoints (ties: lower index),
+ * un-crops, EPnP-RANSAC, LM with maxval weights (weighted != 0) -> pose7 [B,7] f32, rt6 [B,6]. */
+int epb_pose_pipeline(const float* preds, const float* maxvals, const double* bbox_xy,
+                      const double* rate, const double* p3d_model, const double* Kmat, int B, int K,
+                      int min_k, double sel_thresh, int weighted, float* pose7, double* rt6,
+                      double* epnp_rt34, int32_t* status, void* stream);
+
+/* demo.py:295-310: pose7 pred/gt [B,7] f32 -> score_t [B], score_r [B] f64. */
+int epb_esa_score(const float* pose7_pred, const float* pose7_gt, int B, double* score_t,
+                  double* score_r, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESA_POSE_B200_H_ */

@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- poses/s of the post-network pose hot path on BASELINE.json config[1]:
+batch of 64 crops 256x256, 11-keypoint vector fields, 512 RANSAC hypotheses, voting (v3) +
+EPnP-RANSAC + LM on each B200; images shard by batch across GPUs (weak scaling), one NCCL
+all_gather of the [64,7] poses per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference ...                            the reference algorithm on host cores
+Prints ONE JSON line (rank 0).  A "step" = one pass of the hot path over one batch per GPU.
+`value` is timed with inputs resident in HBM; `e2e` goes through the public Python API with
+pinned HOST buffers (H2D of mask + field and D2H of the poses inside the timed region).
+Only the `cpu_baseline` / `--impl reference` legs touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "poses/sec (vector fields -> refined pose)"
+UNIT = "poses/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--vn", type=int, default=11)
+    ap.add_argument("--hn", type=int, default=512)
+    ap.add_argument("--fg", type=float, default=0.25, help="foreground fraction of each crop")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("config[1]: batch %d crops %dx%d, %d-keypoint vector fields, %d RANSAC hypotheses, "
+            "voting(v3)+EPnP-RANSAC+LM, foreground %.2f (tn~%d px/img)"
+            % (a.batch, a.size, a.size, a.vn, a.hn, a.fg, int(a.fg * a.size * a.size)))
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def make_batch_numpy(a, seed, n_images):
+    """Structured SPEED-like crops: the 11 keypoints are the projections of the Tango model under a
+    random pose, scaled into the crop; field = unit vectors towards them + 2 deg noise."""
+    from tests.synth import ellipse_mask, make_pose_case, tango_model
+    rng = np.random.default_rng(seed)
+    s, vn = a.size, a.vn
+    model = tango_model(vn, seed=9)
+    ys, xs = np.mgrid[0:s, 0:s].astype(np.float32)
+    mask = np.zeros((n_images, s, s), np.uint8)
+    vertex = np.zeros((n_images, 2 * vn, s, s), np.float32)
+    kcrop = np.zeros((n_images, vn, 2))
+    geom = np.zeros((n_images, 3))      # bbox x, bbox y, rate  (val.py:180 un-crop: ori = pred/rate + (x, y))
+    for i in range(n_images):
+        c = make_pose_case(seed * 100003 + i, vn, 0.0, 0, model=model)
+        lo, hi = c["p2d"].min(0), c["p2d"].max(0)
+        size = (hi - lo).max() * 1.6 + 8
+        org = (lo + hi) / 2 - size / 2
+        rate = s / size
+        kc = (c["p2d"] - org) * rate
+        kcrop[i] = kc
+        geom[i] = (org[0], org[1], rate)
+        mask[i] = ellipse_mask(s, s, a.fg, rng, jitter=0.03)
+        for v in range(vn):
+            ang = np.arctan2(kc[v, 1] - ys, kc[v, 0] - xs) + np.float32(np.deg2rad(2.0)) * rng.standard_normal((s, s), dtype=np.float32)
+            vertex[i, 2 * v] = np.cos(ang)
+            vertex[i, 2 * v + 1] = np.sin(ang)
+    return mask, vertex, model, geom, kcrop
+
+
+def tile_to(arr, n):
+    reps = (n + arr.shape[0] - 1) // arr.shape[0]
+    return np.concatenate([arr] * reps, 0)[:n]
+
+
+# ----------------------------------------------------------------------------- reference arm
+def _cpu_one(args):
+    """One image through the reference algorithm on one core (oracle = CPU restatement)."""
+    mask, vertex_hwvn2, model, geom, hn, seed = args
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import pose as opose, voting as ov
+    from tests.synth import ESA_K
+    k = ov.ransac_voting_layer_v3(mask[None], vertex_hwvn2[None], hn, idxs_fn=ov.default_idxs_fn(seed))[0]
+    p2d = k.astype(np.float64) * (1.0 / geom[2]) + geom[:2]           # val.py:180
+    rt = opose.pnp(model, p2d, ESA_K, cv2.SOLVEPNP_EPNP)
+    r_exp, _ = cv2.Rodrigues(rt[:, :3])
+    cam = np.concatenate([r_exp.reshape(3), rt[:, 3]])
+    cam = opose.cpnp(model, p2d, ESA_K, cam)
+    return cam
+
+
+def cpu_run(a, n_images, cores, seed=1):
+    """Times n_images of the workload through the oracle on `cores` processes -> (poses/s, seconds)."""
+    import multiprocessing as mp
+    from tests.synth import vertex_hwvn2
+    base = min(n_images, 4)
+    mask, vertex, model, geom, _ = make_batch_numpy(a, seed, base)
+    vx = vertex_hwvn2(vertex)
+    jobs = [(mask[i % base], vx[i % base], model, geom[i % base], a.hn, i) for i in range(n_images)]
+    from oracle import _lib as olib
+    olib.oracle_lib()
+    if cores <= 1:
+        t0 = time.perf_counter()
+        for j in jobs:
+            _cpu_one(j)
+        dt = time.perf_counter() - t0
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_one, jobs[:cores])          # warm the workers
+            t0 = time.perf_counter()
+            pool.map(_cpu_one, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = a.cpu_sample or max(cores, 8)
+    for _ in range(min(a.warmup, 1)):
+        cpu_run(a, cores, cores)
+    t_all, n_all = 0.0, 0
+    for _ in range(a.steps):
+        _, dt = cpu_run(a, per_step, cores)
+        t_all += dt; n_all += per_step
+    value = n_all / t_all
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_all / max(a.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(a), "sample_images_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d images/step of the same workload through oracle/ (C voting restatement, "
+                                       "cv2 EPnP-RANSAC, LM restatement), one process per core" % per_step},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().strip().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from esa_pose_estimation_b200 import _lib, pipeline, ransac_voting_gpu as rv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device and no CPU fallback (use --impl reference for the host arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    # --- data: 8 distinct structured crops per rank, tiled to the batch (content repeats, the
+    # working set per step -- 369 MB of field at the default size -- is larger than the 126 MB L2)
+    base = min(a.batch, 8)
+    from tests.synth import ESA_K
+    mask_np, vertex_np, model_np, geom_np, kcrop_np = make_batch_numpy(a, 11 + rank, base)
+    mask_np, vertex_np, geom_np = tile_to(mask_np, a.batch), tile_to(vertex_np, a.batch), tile_to(geom_np, a.batch)
+    kcrop_np = tile_to(kcrop_np, a.batch)
+    mask_h = torch.from_numpy(mask_np).pin_memory()
+    vertex_h = torch.from_numpy(vertex_np).pin_memory()
+    mask_d, vertex_d = mask_h.to(dev), vertex_h.to(dev)
+    model_d = torch.from_numpy(model_np).to(dev)
+    K_d = torch.from_numpy(ESA_K).to(dev)
+    bbox_d = torch.from_numpy(np.ascontiguousarray(geom_np[:, :2])).to(dev)
+    rate_d = torch.from_numpy(np.ascontiguousarray(geom_np[:, 2])).to(dev)
+    pose_h = torch.empty((a.batch, 7), dtype=torch.float32).pin_memory()
+    torch.manual_seed(1234 + rank)
+
+    def step_device():
+        out = pipeline.poses_from_vertex(mask_d, rv.vertex_layer_reshape(vertex_d), model_d, K_d,
+                                         round_hyp_num=a.hn, bbox_xy=bbox_d, rate=rate_d, sync_rng=False)
+        step_device.kpts = out["kpts"]
+        return pipeline.gather_poses(out["pose7"], a.batch * world) if world > 1 else out["pose7"]
+
+    def step_e2e():
+        m = mask_h.to(dev, non_blocking=True)
+        v = vertex_h.to(dev, non_blocking=True)
+        out = pipeline.poses_from_vertex(m, rv.vertex_layer_reshape(v), model_d, K_d, round_hyp_num=a.hn,
+                                         bbox_xy=bbox_d, rate=rate_d, sync_rng=False)
+        p = pipeline.gather_poses(out["pose7"], a.batch * world) if world > 1 else out["pose7"]
+        pose_h.copy_(p[rank * a.batch:(rank + 1) * a.batch] if world > 1 else p, non_blocking=True)
+        return p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(a.warmup, 3)):
+        last = step_device()
+    barrier()
+    # sanity: poses finite, keypoints recovered (not part of the timed region)
+    assert torch.isfinite(last).all(), "non-finite poses"
+    kerr = float((step_device.kpts.double().cpu() - torch.from_numpy(kcrop_np)).abs().max())
+    assert kerr < 1.0, "voting did not recover the planted keypoints (max err %.3f px)" % kerr
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.epb_profile_enable(1)
+    launches0 = lib.epb_launch_count()
+    ms_dev = timed(step_device, a.steps)
+    launches = lib.epb_launch_count() - launches0
+    prof = {}
+    for cls, name in ((0, "compaction"), (1, "hypothesis"), (2, "vote_count"), (3, "winner_refine"), (4, "pose")):
+        tot, n = _lib.c_double(0), _lib.c_int(0)
+        lib.epb_profile_read(cls, tot, n)
+        prof[name] = (tot.value, n.value)
+    lib.epb_profile_enable(0)
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    poses_per_step = a.batch * world
+    value = poses_per_step * a.steps / (ms_dev * 1e-3)
+    e2e = poses_per_step * a.steps / (ms_e2e * 1e-3)
+    h2d = int(mask_h.numel() + vertex_h.numel() * 4) * world
+    d2h = int(pose_h.numel() * 4) * world
+
+    # --- roofline of the dominant kernel (vote_count), measured live with CUDA events
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    vote_ms, vote_n = prof["vote_count"]
+    per_launch_s = vote_ms * 1e-3 / max(vote_n, 1)
+    alg_bytes = a.batch * a.size * a.size * (8 * a.vn + 1)              # H*W*(8vn+1) per image
+    achieved = alg_bytes / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+    tn = float(mask_np.reshape(a.batch, -1).sum(1).mean())
+    evals = a.batch * a.hn * a.vn * tn
+    sm_count, clk = _lib.c_int(0), _lib.c_int(0)
+    lib.epb_device_info(sm_count, clk, None)
+    sm_mhz = (clocks or {}).get("sm_mhz") or clk.value / 1e3
+    lane_ops_peak = sm_count.value * 128 * sm_mhz * 1e6                  # FP32 lane-ops/s at the observed clock
+    step_ms = ms_dev / a.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "tn_mean": tn, "rng": "philox (torch layout)",
+                   "l2_policy": "inputs larger than L2 (%.0f MB of vector field per step)" % (vertex_h.numel() * 4 / 1e6),
+                   "parallelism": "images sharded by batch, 1 NCCL all_gather of poses" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "vote_count_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_s * 1e3,
+                     "share_of_step": (vote_ms / a.steps) / step_ms if step_ms > 0 else None,
+                     "note": "FP32-ALU-bound at this foreground (SURVEY 8d): see alu",
+                     "alu": {"pair_tests_per_launch": evals, "pair_tests_per_s": evals / per_launch_s if per_launch_s else 0,
+                             "fp32_lane_ops_peak_per_s": lane_ops_peak,
+                             "lane_ops_per_test_at_peak": lane_ops_peak * per_launch_s / evals if evals else None}},
+        "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
+        "clocks": clocks,
+    }
+    # --- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
+    if world == 1:
+        cores = os.cpu_count() or 1
+        n_img = a.cpu_sample or max(2 * cores, 8)
+        try:
+            v, dt = cpu_run(a, n_img, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d images of the same workload through oracle/ in %.1f s" % (n_img, dt)}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "failed: %r" % (e,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -45,6 +45,8 @@ SIGNATURES = {
     "epb_last_cuda_error_string": (ctypes.c_char_p, []),
     "epb_launch_count": (c_ull, []),
     "epb_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_size_t)]),
+    "epb_profile_enable": (c_int, [c_int]),
+    "epb_profile_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
     "epb_decode_heatmaps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "epb_refine_keypoints": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "epb_generate_hypothesis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -28,6 +28,18 @@ inline int check_api(cudaError_t e) {
   return EPB_OK;
 }
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline):
+// enabled by epb_profile_enable(); otherwise a no-op.
+enum { PROF_COMPACT = 0, PROF_HYPOTHESIS = 1, PROF_VOTE_COUNT = 2, PROF_REFINE = 3, PROF_POSE = 4,
+       PROF_DECODE = 5, PROF_CLASSES = 6 };
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, cudaStream_t s);
+struct ProfScope {
+  int cls; cudaStream_t s;
+  ProfScope(int c, cudaStream_t st) : cls(c), s(st) { prof_begin(cls, s); }
+  ~ProfScope() { prof_end(cls, s); }
+};
+
 #define EPB_RETURN_IF(expr)            \
   do {                                 \
     int _s = (expr);                   \

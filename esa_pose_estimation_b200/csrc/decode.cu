@@ -158,6 +158,7 @@ extern "C" int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, in
   if (!hm || n_maps < 0 || H <= 0 || W <= 0 || (long long)H * W > 0x7fffffffLL) return EPB_ERR_INVALID;
   if (n_maps == 0) return EPB_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(PROF_DECODE, s);
   if (H * W <= 64 * 64) {
     constexpr int BLOCK = 128;
     decode_kernel<32, BLOCK><<<(n_maps + 3) / 4, BLOCK, 0, s>>>(hm, n_maps, H, W, flags, xy, maxval, idx);

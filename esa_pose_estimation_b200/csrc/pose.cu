@@ -983,6 +983,7 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
     return EPB_ERR_INVALID;
   if (!pose7 && !rt6) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
+  ProfScope ps(PROF_POSE, (cudaStream_t)stream);
   pose_pipeline_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
       preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6,
       epnp_rt34, status);

@@ -960,6 +960,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   // the subsample can only trigger when an image can hold more than max_num foreground pixels
   const int allow_sub = (HW > p.max_num) && (io->selection || sc.use_philox);
 
+  prof_begin(PROF_COMPACT, s);
   mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 0, ws, sc);
   EPB_RETURN_IF(check_launch());
   mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 0, p.min_num, p.max_num, allow_sub, ws);
@@ -975,6 +976,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   }
   mask_scatter_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc);
   EPB_RETURN_IF(check_launch());
+  prof_end(PROF_COMPACT, s);
   if (io->tn_out)
     EPB_RETURN_IF(check_api(cudaMemcpyAsync(io->tn_out, ws.tn, (size_t)p.B * 4, cudaMemcpyDeviceToDevice, s)));
 
@@ -986,6 +988,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   hc.inc_r = lr.inc;
   {
     const long long n = (long long)p.B * HN * p.vn;
+    ProfScope ps(PROF_HYPOTHESIS, s);
     hypothesis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(io->vertex, p, ws, hc, io->hyp);
     EPB_RETURN_IF(check_launch());
   }
@@ -1007,6 +1010,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     if (use_atomic)
       EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
     dim3 grid(splits, p.vn * chunks, p.B);
+    ProfScope ps(PROF_VOTE_COUNT, s);
     if (R == 1) vote_count_kernel<1><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
     else if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
     else vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
@@ -1017,6 +1021,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     counts_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, ws, io->counts);
     EPB_RETURN_IF(check_launch());
   }
+  ProfScope ps_tail(PROF_REFINE, s);
   if (is_layer) {
     winner_refine_kernel<<<dim3(p.vn, p.B), 256, 0, s>>>(io->vertex, p, ws, io->pts, io->var_or_conf,
                                                          io->status);

@@ -55,6 +55,13 @@ unsigned long long epb_launch_count(void);
 /* SM count / clock of the current device (roofline reporting). */
 int epb_device_info(int* sm_count, int* sm_clock_khz, size_t* l2_bytes);
 
+/* Optional timing of kernel classes with CUDA events on the launching stream (bench.py roofline).
+ * Classes: 0 compaction, 1 hypothesis, 2 vote_count, 3 refine/distribution, 4 pose, 5 decode.
+ * epb_profile_enable(1) starts recording; epb_profile_read() synchronises the recorded events and
+ * returns their summed duration / count; epb_profile_enable(0) stops and frees them. */
+int epb_profile_enable(int on);
+int epb_profile_read(int cls, double* total_ms, int* launches);
+
 /* ------------------------------------------------------------------ heatmap decode (a1,a2) */
 enum {
   EPB_DECODE_REFINE = 1,        /* log-domain sub-pixel step of inference.py:75-94 */

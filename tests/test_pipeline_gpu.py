@@ -1,0 +1,71 @@
+"""End-to-end GPU paths: heatmaps -> pose (val.py flow) and vector field -> voting -> pose, against
+the oracle on identical inputs, plus __graft_entry__.smoke()."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as odec
+from oracle import pose as opose
+from oracle import voting as ov
+from tests.synth import ESA_K, make_heatmaps, make_pose_case, make_vertex_field, rodrigues, tango_model, vertex_hwvn2
+
+pytestmark = pytest.mark.gpu
+
+
+def _ang(r1, r2):
+    c = (np.trace(r1 @ r2.T) - 1) / 2
+    return np.degrees(np.arccos(np.clip(c, -1, 1)))
+
+
+def test_heatmaps_to_pose_matches_oracle(cuda_dev):
+    from esa_pose_estimation_b200 import pipeline
+    B, kp, S = 6, 11, 128
+    model = tango_model(kp, seed=9)
+    hms = np.zeros((B, kp, S, S), np.float32); bbox = np.zeros((B, 2)); rate = np.zeros(B)
+    ys, xs = np.mgrid[0:S, 0:S].astype(np.float64)
+    rng = np.random.default_rng(3)
+    for i in range(B):
+        c = make_pose_case(9000 + i, kp, 0.0, 0, model=model)
+        lo, hi = c["p2d"].min(0), c["p2d"].max(0)
+        size = (hi - lo).max() * 1.3 + 8
+        bbox[i] = (lo + hi) / 2 - size / 2
+        rate[i] = S / size
+        crop = (c["p2d"] - bbox[i]) * rate[i]
+        for k in range(kp):
+            g = np.exp(-((xs - crop[k, 0]) ** 2 + (ys - crop[k, 1]) ** 2) / 8.0) * rng.uniform(0.6, 1.0)
+            hms[i, k] = (g + rng.normal(0, 0.01, (S, S))).astype(np.float32)
+    out = pipeline.poses_from_heatmaps(torch.from_numpy(hms).to(cuda_dev), torch.from_numpy(bbox).to(cuda_dev),
+                                       torch.from_numpy(rate).to(cuda_dev), torch.from_numpy(model).to(cuda_dev),
+                                       torch.from_numpy(ESA_K).to(cuda_dev), min_k=8)
+    rt6 = out["rt6"].cpu().numpy(); pose7 = out["pose7"].cpu().numpy()
+    for i in range(B):
+        preds, maxvals, _ = odec.decode_frame(hms[i:i + 1])
+        o = opose.frame_pose(preds, maxvals, bbox[i], rate[i], model, ESA_K, min_k=8)
+        assert _ang(rodrigues(rt6[i, :3]), o["pose34"][:, :3]) < 1e-3
+        assert np.linalg.norm(rt6[i, 3:] - o["t"]) / np.linalg.norm(o["t"]) < 1e-4
+        assert min(np.abs(pose7[i, :4] - o["q"]).max(), np.abs(pose7[i, :4] + o["q"]).max()) < 1e-5
+
+
+def test_vertex_to_pose_matches_oracle(cuda_dev):
+    from esa_pose_estimation_b200 import pipeline, ransac_voting_gpu as rv
+    B, vn, S, hn = 4, 11, 96, 256
+    mask, vertex, kpts = make_vertex_field(61, B, S, S, vn, 0.35, noise_deg=1.5)
+    vx = vertex_hwvn2(vertex)
+    model = tango_model(vn, seed=9)
+    fn = ov.default_idxs_fn(3)
+    idxs = np.zeros((B, 1, hn, vn, 2), np.int32)
+    for bi in range(B):
+        idxs[bi, 0] = fn(bi, 0, hn, vn, int((mask[bi] != 0).sum()))
+    K = np.array([[120.0, 0, 48], [0, 120.0, 48], [0, 0, 1]])
+    out = pipeline.poses_from_vertex(torch.from_numpy(mask).to(cuda_dev),
+                                     rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev)),
+                                     torch.from_numpy(model).to(cuda_dev), torch.from_numpy(K).to(cuda_dev),
+                                     round_hyp_num=hn, idxs=torch.from_numpy(idxs).to(cuda_dev))
+    k_o = ov.ransac_voting_layer_v3(mask, vx, hn, idxs_fn=fn)
+    np.testing.assert_allclose(out["kpts"].cpu().numpy(), k_o, atol=1e-3)
+    assert out["pose7"].shape == (B, 7) and out["status"].shape == (B,)
+
+
+def test_smoke_entry(cuda_dev):
+    import __graft_entry__ as g
+    g.smoke()

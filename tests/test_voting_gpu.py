@@ -1,0 +1,252 @@
+"""GPU parity for csrc/voting.cu through the C ABI:
+  * our kernels and the C restatement against the reference's own kernels compiled verbatim for
+    sm_100a (oracle/_ref/libref_voting.so): hypothesis points and inlier bytes bit-exact;
+  * the fused batched driver against the oracle driver on identical indices: counts bit-exact,
+    refined keypoints within 1e-3 px;
+  * the in-kernel Philox stream against torch's own random_/uniform_ draws.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import _lib as olib
+from oracle import voting as ov
+from tests.synth import make_vertex_field, vertex_hwvn2
+
+pytestmark = pytest.mark.gpu
+
+
+def _compact_case(seed, h, w, vn, frac, kind="structured"):
+    mask, vertex, kpts = make_vertex_field(seed, 1, h, w, vn, frac, kind)
+    vx = vertex_hwvn2(vertex)
+    _, coords, direct = ov.compact(mask[0] != 0, vx[0], 10 ** 9, ov.default_selection_fn(0), 0)
+    return coords, direct
+
+
+def _ref_lib():
+    lib = olib.ref_voting_lib(required=False)
+    if lib is None:
+        pytest.skip("oracle/_ref/libref_voting.so not built")
+    return lib
+
+
+def _dp(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("kind,seed", [("structured", 1), ("randinit", 2), ("structured", 3)])
+def test_primitives_bit_exact_vs_reference_kernels(cuda_dev, kind, seed):
+    from esa_pose_estimation_b200 import ransac_voting
+    ref = _ref_lib()
+    coords, direct = _compact_case(seed, 48, 56, 5, 0.6, kind)
+    tn, vn, _ = direct.shape
+    hn = 96
+    rng = np.random.default_rng(seed)
+    idxs = rng.integers(0, tn, (hn, vn, 2)).astype(np.int32)
+    idxs[0, :, 1] = idxs[0, :, 0]                                      # same pixel twice: parallel rays
+    d_t, c_t, i_t = (torch.from_numpy(a).to(cuda_dev) for a in (direct, coords, idxs))
+    # reference kernels (device oracle)
+    hyp_ref = torch.zeros((hn, vn, 2), device=cuda_dev)
+    assert ref.ref_generate_hypothesis(_dp(d_t), _dp(c_t), _dp(i_t), _dp(hyp_ref), tn, vn, hn) == 0
+    torch.cuda.synchronize()
+    hyp = ransac_voting.generate_hypothesis(d_t, c_t, i_t)
+    hyp_c = ov.generate_hypothesis(direct, coords, idxs)
+    assert torch.equal(hyp.view(torch.int32), hyp_ref.view(torch.int32))          # ours == reference, bitwise
+    np.testing.assert_array_equal(hyp_c.view(np.int32), hyp_ref.cpu().numpy().view(np.int32))  # C oracle too
+    for thresh in (0.999, 0.99, 0.5):
+        inl_ref = torch.zeros((hn, vn, tn), dtype=torch.uint8, device=cuda_dev)
+        assert ref.ref_voting_for_hypothesis(_dp(d_t), _dp(c_t), _dp(hyp_ref), _dp(inl_ref), tn, vn, hn,
+                                             ctypes.c_float(thresh)) == 0
+        torch.cuda.synchronize()
+        inl = torch.zeros((hn, vn, tn), dtype=torch.uint8, device=cuda_dev)
+        ransac_voting.voting_for_hypothesis(d_t, c_t, hyp_ref, inl, thresh)
+        assert torch.equal(inl, inl_ref)
+        inl_c = np.zeros((hn, vn, tn), np.uint8)
+        ov.voting_for_hypothesis(direct, coords, hyp_ref.cpu().numpy(), inl_c, thresh)
+        np.testing.assert_array_equal(inl_c, inl_ref.cpu().numpy())
+
+
+def test_pybind_level_checks(cuda_dev):
+    from esa_pose_estimation_b200 import ransac_voting
+    d = torch.zeros((8, 2, 2), device=cuda_dev)
+    c = torch.zeros((8, 2), device=cuda_dev)
+    i = torch.zeros((4, 2, 2), dtype=torch.int32, device=cuda_dev)
+    with pytest.raises(RuntimeError):
+        ransac_voting.generate_hypothesis(d.cpu(), c, i)               # CHECK_CUDA
+    with pytest.raises(RuntimeError):
+        ransac_voting.generate_hypothesis(d.transpose(0, 1), c, i)     # CHECK_CONTIGUOUS
+    hyp = ransac_voting.generate_hypothesis(d, c, i)
+    assert hyp.shape == (4, 2, 2) and (hyp == 0).all()                 # degenerate pairs stay zero
+
+
+def _idxs_for(mask, vx, hn, rounds, max_num, seed, eq1=False):
+    """Per-image indices drawn exactly as the oracle's idxs_fn will see them."""
+    b, h, w, vn, _ = vx.shape
+    fn = ov.default_idxs_fn(seed)
+    sel = ov.default_selection_fn(seed)
+    out = np.zeros((b, rounds, hn, vn, 2), np.int32)
+    selection = np.zeros((b, h, w), np.float32)
+    for bi in range(b):
+        cur = (mask[bi] == 1) if eq1 else (mask[bi] != 0)
+        selection[bi] = sel(bi, h, w)
+        if cur.sum() < 5:
+            continue
+        _, coords, _ = ov.compact(cur, vx[bi], max_num, sel, bi)
+        for r in range(rounds):
+            out[bi, r] = fn(bi, r, hn, vn, coords.shape[0])
+    return out, selection, fn, sel
+
+
+@pytest.mark.parametrize("layout", ["nchw_view", "contiguous"])
+@pytest.mark.parametrize("cfg", [dict(b=3, h=64, w=72, vn=4, hn=128, frac=0.3, max_num=30000),
+                                 dict(b=2, h=96, w=96, vn=11, hn=512, frac=0.5, max_num=30000),
+                                 dict(b=2, h=80, w=64, vn=3, hn=64, frac=1.0, max_num=1500),
+                                 dict(b=2, h=33, w=47, vn=2, hn=300, frac=0.4, max_num=30000)])
+def test_layer_v3_v4_v5_match_oracle(cuda_dev, cfg, layout):
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    b, h, w, vn, hn = cfg["b"], cfg["h"], cfg["w"], cfg["vn"], cfg["hn"]
+    mask, vertex, kpts = make_vertex_field(11 + hn, b, h, w, vn, cfg["frac"])
+    mask[-1, :, : w // 2] = 0                                            # ragged foreground
+    vx = vertex_hwvn2(vertex)
+    idxs, selection, fn, sel = _idxs_for(mask, vx, hn, 1, cfg["max_num"], 5)
+    v_t = torch.from_numpy(vertex).to(cuda_dev)
+    vert = rv.vertex_layer_reshape(v_t) if layout == "nchw_view" else torch.from_numpy(vx).to(cuda_dev)
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    kw = dict(idxs=torch.from_numpy(idxs).to(cuda_dev), selection=torch.from_numpy(selection).to(cuda_dev))
+    # fused driver, everything it computes
+    dbg = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn, inlier_thresh=0.999, max_num=cfg["max_num"], **kw)
+    hyp_o, cnt_o = ov.ransac_voting_hypothesis((mask != 0).astype(np.uint8), vx, hn, 0.999, max_num=cfg["max_num"],
+                                               idxs_fn=fn, selection_fn=sel)
+    np.testing.assert_array_equal(dbg["hyp"].cpu().numpy().view(np.int32), hyp_o.view(np.int32))   # bit-exact
+    np.testing.assert_array_equal(dbg["counts"].cpu().numpy(), cnt_o)                               # bit-exact
+    p3_o = ov.ransac_voting_layer_v3(mask, vx, hn, max_num=cfg["max_num"], idxs_fn=fn, selection_fn=sel)
+    p3 = rv.ransac_voting_layer_v3(m_t, vert, hn, max_num=cfg["max_num"], **kw).cpu().numpy()
+    np.testing.assert_allclose(p3, p3_o, rtol=0, atol=1e-3)
+    p4_o, var_o = ov.ransac_voting_layer_v4(mask, vx, hn, max_num=cfg["max_num"], idxs_fn=fn, selection_fn=sel)
+    p4, var = rv.ransac_voting_layer_v4(m_t, vert, hn, max_num=cfg["max_num"], **kw)
+    np.testing.assert_allclose(p4.cpu().numpy(), p4_o, rtol=0, atol=1e-3)
+    np.testing.assert_allclose(var.cpu().numpy(), var_o, rtol=1e-3, atol=1e-6)
+    mx5 = min(cfg["max_num"], 400)
+    idxs5, selection5, fn5, sel5 = _idxs_for(mask, vx, hn, 1, mx5, 6)
+    kw5 = dict(idxs=torch.from_numpy(idxs5).to(cuda_dev), selection=torch.from_numpy(selection5).to(cuda_dev))
+    p5_o, conf_o = ov.ransac_voting_layer_v5(mask, vx, hn, max_num=mx5, idxs_fn=fn5, selection_fn=sel5)
+    p5, conf = rv.ransac_voting_layer_v5(m_t, vert, hn, max_num=mx5, **kw5)
+    np.testing.assert_allclose(p5.cpu().numpy(), p5_o, rtol=0, atol=1e-3)
+    np.testing.assert_allclose(conf.cpu().numpy(), conf_o, rtol=0, atol=1e-6)
+
+
+def test_degenerate_and_thresholds(cuda_dev):
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    mask, vertex, _ = make_vertex_field(21, 3, 40, 40, 3, 0.4, "randinit")
+    mask[1] = 0
+    mask[1, 0, :3] = 1                                                   # < min_num
+    mask[2] = 0                                                          # empty
+    vx = vertex_hwvn2(vertex)
+    idxs, selection, fn, sel = _idxs_for(mask, vx, 64, 1, 30000, 9)
+    vert = torch.from_numpy(vx).to(cuda_dev)
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    kw = dict(idxs=torch.from_numpy(idxs).to(cuda_dev))
+    p3 = rv.ransac_voting_layer_v3(m_t, vert, 64, **kw)
+    assert (p3[1:] == 0).all()
+    _, var = rv.ransac_voting_layer_v4(m_t, vert, 64, **kw)
+    assert (var[1:] == 1).all()
+    _, conf = rv.ransac_voting_layer_v5(m_t, vert, 64, max_num=30000, **kw)
+    assert (conf[1:] == 0).all()
+    hyp, cnt = rv.ransac_voting_hypothesis(m_t, vert, 64, **kw)
+    assert (hyp[1:] == 0).all() and (cnt[1:] == 1).all() and cnt.dtype == torch.int64
+    # thresholds outside the fast-filter range take the exact path: still bit-exact counts
+    for thr in (0.0, -0.5, 1e-4, 0.2, 0.999999):
+        _, c = rv.ransac_voting_hypothesis(m_t, vert, 64, inlier_thresh=thr, **kw)
+        _, c_o = ov.ransac_voting_hypothesis(mask, vx, 64, thr, idxs_fn=fn, selection_fn=sel)
+        np.testing.assert_array_equal(c.cpu().numpy(), c_o)
+
+
+def test_distribution_matches_oracle(cuda_dev):
+    from esa_pose_estimation_b200 import ransac_voting_gpu as rv
+    b, h, w, vn = 2, 64, 64, 5
+    mask, vertex, kpts = make_vertex_field(31, b, h, w, vn, 0.5, noise_deg=1.5)
+    vx = vertex_hwvn2(vertex)
+    rounds, hn = 4, 64
+    idxs, selection, fn, sel = _idxs_for(mask, vx, hn, rounds, 30000, 12, eq1=True)
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev))
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    kw = dict(idxs=torch.from_numpy(idxs).to(cuda_dev))
+    mean, cov = rv.estimate_voting_distribution(m_t, vert, round_hyp_num=hn, min_hyp_num=hn * rounds, topk=32, **kw)
+    mean_o, cov_o = ov.estimate_voting_distribution(mask, vx, hn, hn * rounds, 32, idxs_fn=fn, selection_fn=sel)
+    np.testing.assert_allclose(mean.cpu().numpy(), mean_o, rtol=0, atol=1e-3)
+    np.testing.assert_allclose(cov.cpu().numpy(), cov_o, rtol=1e-4, atol=1e-4)
+    m2, cov2 = rv.estimate_voting_distribution_with_mean(m_t, vert, mean, round_hyp_num=hn, min_hyp_num=hn * rounds, **kw)
+    _, cov2_o = ov.estimate_voting_distribution_with_mean(mask, vx, mean_o, hn, hn * rounds, idxs_fn=fn, selection_fn=sel)
+    np.testing.assert_allclose(cov2.cpu().numpy(), cov2_o, rtol=1e-4, atol=1e-4)
+
+
+def test_philox_matches_torch_generator(cuda_dev):
+    """Hypothesis indices regenerated in-kernel equal torch's random_(0, tn) under the same seed, in
+    the reference's per-image call order, including the uniform_ subsample draw; and the generator
+    ends where the reference's would."""
+    from esa_pose_estimation_b200 import ransac_voting_gpu as rv
+    b, h, w, vn, hn = 3, 48, 40, 4, 96
+    mask, vertex, _ = make_vertex_field(41, b, h, w, vn, 0.8, "randinit")
+    mask[1] = 0                                                          # skipped image consumes nothing
+    vx = vertex_hwvn2(vertex)
+    max_num = 700                                                        # forces the subsample on image 0 and 2
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    vert = torch.from_numpy(vx).to(cuda_dev)
+    # reference call order with torch itself (ransac_voting_gpu.py:527-547)
+    torch.manual_seed(1234)
+    idxs_ref = np.zeros((b, 1, hn, vn, 2), np.int32)
+    sel_ref = np.zeros((b, h, w), np.float32)
+    for bi in range(b):
+        cur = m_t[bi].byte()
+        fg = torch.sum(cur)
+        if fg < 5:
+            continue
+        if fg > max_num:
+            selection = torch.zeros(cur.shape, dtype=torch.float32, device=cuda_dev).uniform_(0, 1)
+            sel_ref[bi] = selection.cpu().numpy()
+            cur = cur * (selection < (max_num / fg.float()))
+        tn = int(torch.nonzero(cur).shape[0])
+        idxs_ref[bi, 0] = torch.zeros([hn, vn, 2], dtype=torch.int32, device=cuda_dev).random_(0, tn).cpu().numpy()
+    end_offset = torch.cuda.default_generators[0].get_offset()
+    after_ref = torch.rand(4, device=cuda_dev).cpu()
+    # explicit-index run
+    hyp_a, cnt_a = rv.ransac_voting_hypothesis(m_t, vert, hn, max_num=max_num,
+                                               idxs=torch.from_numpy(idxs_ref).to(cuda_dev),
+                                               selection=torch.from_numpy(sel_ref).to(cuda_dev))
+    # Philox run under the same seed
+    torch.manual_seed(1234)
+    hyp_b, cnt_b = rv.ransac_voting_hypothesis(m_t, vert, hn, max_num=max_num)
+    assert torch.cuda.default_generators[0].get_offset() == end_offset
+    after = torch.rand(4, device=cuda_dev).cpu()
+    assert torch.equal(hyp_a.view(torch.int32), hyp_b.view(torch.int32))
+    assert torch.equal(cnt_a, cnt_b)
+    assert torch.equal(after, after_ref)
+
+
+def test_full_size_properties(cuda_dev):
+    """BASELINE config 2 size (64 x 256x256, vn=11, hn=512): properties instead of a full oracle pass."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    b, h, w, vn, hn = 64, 256, 256, 11, 512
+    mask, vertex, kpts = make_vertex_field(51, 4, h, w, vn, 0.25, noise_deg=2.0)
+    mask = np.tile(mask, (16, 1, 1)); vertex = np.tile(vertex, (16, 1, 1, 1)); kpts = np.tile(kpts, (16, 1, 1))
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev))
+    torch.manual_seed(7)
+    dbg = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn)
+    tn = dbg["tn"].cpu().numpy()
+    np.testing.assert_array_equal(tn, mask.reshape(b, -1).sum(1))
+    cnt = dbg["counts"].cpu().numpy()
+    assert cnt.min() >= 0 and (cnt.max(axis=(1, 2)) <= tn).all()
+    pts = dbg["pts"].cpu().numpy()
+    assert np.abs(pts - kpts).max() < 0.5                               # recovers the planted keypoints
+    # one image checked exactly against the oracle using the counts' own hypotheses
+    vx0 = vertex_hwvn2(vertex[:1])
+    _, coords, direct = ov.compact(mask[0] != 0, vx0[0], 30000, ov.default_selection_fn(0), 0)
+    hyp0 = dbg["hyp"][0].cpu().numpy()
+    np.testing.assert_array_equal(ov.vote_counts(direct, coords, hyp0[:64], 0.999), cnt[0, :64])
+    # same seed -> identical result (determinism, no atomics races in the count)
+    torch.manual_seed(7)
+    dbg2 = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn)
+    assert torch.equal(dbg2["counts"], dbg["counts"]) and torch.equal(dbg2["pts"].view(torch.int32), dbg["pts"].view(torch.int32))

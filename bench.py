@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--hn", type=int, default=512)
     ap.add_argument("--fg", type=float, default=0.25, help="foreground fraction of each crop")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side baseline (profiling runs)")
     return ap.parse_args()
 
 
@@ -341,7 +342,7 @@ def run_ours(a):
         "clocks": clocks,
     }
     # --- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
-    if world == 1:
+    if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
         n_img = a.cpu_sample or max(2 * cores, 8)
         try:

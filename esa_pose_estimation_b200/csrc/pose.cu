@@ -107,17 +107,29 @@ __device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[
   }
 }
 
-// Cyclic Jacobi eigen-decomposition of the symmetric 12x12 in shared memory; lanes 0..11 apply
-// each rotation to one row/column element.  Eigenvectors end up in the columns of V.
+// Parallel-order (Brent-Luk round robin) Jacobi eigen-decomposition of the symmetric 12x12 in shared
+// memory: each of the 11 steps of a sweep applies 6 disjoint rotations at once, A <- J^T A J, with the
+// work spread over all 32 lanes (60 off-diagonal block elements + 72 eigenvector row updates per
+// step).  Every off-diagonal 2x2 block is computed once and mirrored, so A stays exactly symmetric.
+// Eigenvectors end up in the columns of V.  (Validated in numpy, see oracle/epnp_port.py notes.)
+__constant__ unsigned char kJP[11][6] = {{0, 2, 4, 6, 8, 10}, {0, 1, 2, 4, 6, 8}, {0, 3, 1, 2, 4, 6}, {0, 5, 3, 1, 2, 4},
+                                         {0, 7, 5, 3, 1, 2},  {0, 9, 7, 5, 3, 1}, {0, 8, 6, 4, 2, 1}, {0, 6, 4, 2, 1, 3},
+                                         {0, 4, 2, 1, 3, 5},  {0, 2, 1, 3, 5, 7}, {0, 1, 3, 5, 7, 9}};
+__constant__ unsigned char kJQ[11][6] = {{1, 3, 5, 7, 9, 11},  {3, 5, 7, 9, 11, 10}, {5, 7, 9, 11, 10, 8}, {7, 9, 11, 10, 8, 6},
+                                         {9, 11, 10, 8, 6, 4}, {11, 10, 8, 6, 4, 2}, {10, 11, 9, 7, 5, 3}, {8, 10, 11, 9, 7, 5},
+                                         {6, 8, 10, 11, 9, 7}, {4, 6, 8, 10, 11, 9}, {2, 4, 6, 8, 10, 11}};
+__constant__ unsigned char kBA[15] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4};
+__constant__ unsigned char kBB[15] = {1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
 __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
   for (int e = lane; e < 144; e += 32) ws.V[e / 12][e % 12] = (e / 12 == e % 12) ? 1.0 : 0.0;
   __syncwarp();
+  double* cs = ws.S;  // [6][4]: c, s, t, apq of the current step (S is free during the eigen-solve)
   for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0, diag = 0;
+    double off = 0;
     for (int e = lane; e < 144; e += 32) {
       const int r = e / 12, c = e % 12;
-      const double x = ws.A[r][c];
-      if (r < c) off += x * x; else if (r == c) diag += x * x;
+      if (r < c) { const double x = ws.A[r][c]; off += x * x; }
     }
     off = warp_sum(off);
     double dmin = INFINITY;
@@ -125,34 +137,76 @@ __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
     // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the
     // null-space vectors are what EPnP needs); exact null spaces fall through to the absolute test
     if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
-    (void)diag;
-    for (int p = 0; p < 11; ++p)
-      for (int q = p + 1; q < 12; ++q) {
+    for (int step = 0; step < 11; ++step) {
+      // --- rotation angles of the 6 disjoint pairs
+      if (lane < 6) {
+        const int p = kJP[step][lane], q = kJQ[step][lane];
         const double apq = ws.A[p][q];
-        if (apq != 0.0) {   // warp-uniform
-          const double app = ws.A[p][p], aqq = ws.A[q][q];
-          const double theta = (aqq - app) / (2.0 * apq);
-          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-          __syncwarp();
-          if (lane < 12) {
-            const int k = lane;
-            if (k != p && k != q) {
-              const double akp = ws.A[k][p], akq = ws.A[k][q];
-              const double np_ = c * akp - s * akq, nq_ = s * akp + c * akq;
-              ws.A[k][p] = np_; ws.A[p][k] = np_; ws.A[k][q] = nq_; ws.A[q][k] = nq_;
-            }
-            const double vkp = ws.V[k][p], vkq = ws.V[k][q];
-            ws.V[k][p] = c * vkp - s * vkq; ws.V[k][q] = s * vkp + c * vkq;
-          } else if (lane == 12) {
-            ws.A[p][p] = app - t * apq; ws.A[q][q] = aqq + t * apq; ws.A[p][q] = 0.0; ws.A[q][p] = 0.0;
-          }
-          __syncwarp();
+        double c = 1.0, s = 0.0, t = 0.0;
+        if (apq != 0.0) {
+          const double theta = (ws.A[q][q] - ws.A[p][p]) / (2.0 * apq);
+          t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0);
+          s = t * c;
+        }
+        cs[4 * lane] = c; cs[4 * lane + 1] = s; cs[4 * lane + 2] = t; cs[4 * lane + 3] = apq;
+      }
+      __syncwarp();
+      // --- read phase: everything a lane will write is computed into registers first
+      double blk_val[2]; int blk_r[2], blk_c[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int task = lane + 32 * k;   // 60 tasks: 15 blocks x 4 elements
+        blk_r[k] = -1; blk_c[k] = 0; blk_val[k] = 0.0;
+        if (task < 60) {
+          const int blk = task >> 2, e = task & 3, u = e >> 1, w = e & 1;
+          const int a = kBA[blk], b = kBB[blk];
+          const int pa = kJP[step][a], qa = kJQ[step][a], pb = kJP[step][b], qb = kJQ[step][b];
+          const double ca = cs[4 * a], sa = cs[4 * a + 1], cb = cs[4 * b], sb = cs[4 * b + 1];
+          const double b00 = ws.A[pa][pb], b01 = ws.A[pa][qb], b10 = ws.A[qa][pb], b11 = ws.A[qa][qb];
+          // T = Ra^T B (row u), then Bn = T Rb (column w);  Ra = [[ca, sa], [-sa, ca]]
+          const double t0 = u == 0 ? ca * b00 - sa * b10 : sa * b00 + ca * b10;
+          const double t1 = u == 0 ? ca * b01 - sa * b11 : sa * b01 + ca * b11;
+          blk_val[k] = w == 0 ? t0 * cb - t1 * sb : t0 * sb + t1 * cb;
+          blk_r[k] = u == 0 ? pa : qa;
+          blk_c[k] = w == 0 ? pb : qb;
         }
       }
+      double v_p[3], v_q[3]; int v_i[3], v_pp[3], v_qq[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int task = lane + 32 * k;   // 72 tasks: 12 rows of V x 6 pairs
+        v_i[k] = -1; v_pp[k] = 0; v_qq[k] = 0; v_p[k] = 0.0; v_q[k] = 0.0;
+        if (task < 72) {
+          const int i = task / 6, a = task - 6 * i;
+          const int p = kJP[step][a], q = kJQ[step][a];
+          const double c = cs[4 * a], s = cs[4 * a + 1];
+          const double vp = ws.V[i][p], vq = ws.V[i][q];
+          v_p[k] = c * vp - s * vq; v_q[k] = s * vp + c * vq;
+          v_i[k] = i; v_pp[k] = p; v_qq[k] = q;
+        }
+      }
+      double d_pp = 0, d_qq = 0; int d_p = -1, d_q = 0;
+      if (lane < 6) {
+        d_p = kJP[step][lane]; d_q = kJQ[step][lane];
+        const double t = cs[4 * lane + 2], apq = cs[4 * lane + 3];
+        d_pp = ws.A[d_p][d_p] - t * apq;
+        d_qq = ws.A[d_q][d_q] + t * apq;
+      }
+      __syncwarp();
+      // --- write phase
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (blk_r[k] >= 0) { ws.A[blk_r[k]][blk_c[k]] = blk_val[k]; ws.A[blk_c[k]][blk_r[k]] = blk_val[k]; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (v_i[k] >= 0) { ws.V[v_i[k]][v_pp[k]] = v_p[k]; ws.V[v_i[k]][v_qq[k]] = v_q[k]; }
+      if (d_p >= 0) { ws.A[d_p][d_p] = d_pp; ws.A[d_q][d_q] = d_qq; ws.A[d_p][d_q] = 0.0; ws.A[d_q][d_p] = 0.0; }
+      __syncwarp();
+    }
   }
   __syncwarp();
-  // ascending order of the eigenvalues (stable), computed redundantly
+  // ascending order of the eigenvalues (stable)
   if (lane == 0) {
     for (int i = 0; i < 12; ++i) ws.order[i] = i;
     for (int i = 1; i < 12; ++i) {
@@ -748,7 +802,7 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
            unsigned long long* __restrict__ inlier_mask, int32_t* __restrict__ status) {
   __shared__ WarpScratch scratch[POSE_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x * POSE_WARPS + warp;
+  const int img = blockIdx.x * (blockDim.x >> 5) + warp;
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
   const int n = npts ? min(npts[img], n_max) : n_max;
@@ -783,7 +837,7 @@ lm_kernel(const double* __restrict__ p2d, const double* __restrict__ p3d, int p3
           const double* __restrict__ init_rt, const int32_t* __restrict__ npts, int B, int n_max,
           double* __restrict__ result_rt, int32_t* __restrict__ iters, double* __restrict__ final_cost) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x * POSE_WARPS + warp;
+  const int img = blockIdx.x * (blockDim.x >> 5) + warp;
   if (img >= B) return;
   const int n = npts ? min(npts[img], n_max) : n_max;
   const bool active = lane < n;
@@ -849,7 +903,7 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   __shared__ WarpScratch scratch[POSE_WARPS];
   __shared__ double s_pts[POSE_WARPS][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x * POSE_WARPS + warp;
+  const int img = blockIdx.x * (blockDim.x >> 5) + warp;
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
   // --- keypoint selection (val.py:172-177): large_k = max(#(maxval > 0.8), 24), top large_k by maxval
@@ -937,13 +991,21 @@ __global__ void esa_score_kernel(const float* __restrict__ pred, const float* __
 
 using namespace epb;
 
+// one warp per image; small batches get one warp per CTA so that they spread over more SMs
+static inline void pose_launch_shape(int B, int* grid, int* block) {
+  const int warps = B <= 148 * 8 ? 1 : POSE_WARPS;
+  *block = warps * 32;
+  *grid = (B + warps - 1) / warps;
+}
+
 extern "C" int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const double* p2d, const double* K,
                                    int K_batched, const int32_t* npts, int B, int n_max, double reproj_err,
                                    int max_iters, double confidence, double* rt34,
                                    unsigned long long* inlier_mask, int32_t* status, void* stream) {
   if (!p3d || !p2d || !K || !rt34 || B < 0 || n_max <= 0 || n_max > 32 || max_iters < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
-  pnp_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  int grid, block; pose_launch_shape(B, &grid, &block);
+  pnp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       p3d, p3d_batched, p2d, K, K_batched, npts, B, n_max, reproj_err, max_iters, confidence, rt34,
       inlier_mask, status);
   return check_launch();
@@ -956,7 +1018,8 @@ extern "C" int epb_lm_refine(const double* p2d, const double* p3d, int p3d_batch
   if (!p2d || !p3d || !w2d || !K || !init_rt || !result_rt || B < 0 || n_max <= 0 || n_max > 32)
     return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
-  lm_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  int grid, block; pose_launch_shape(B, &grid, &block);
+  lm_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       p2d, p3d, p3d_batched, w2d, K, K_batched, init_rt, npts, B, n_max, result_rt, iters, final_cost);
   return check_launch();
 }
@@ -984,7 +1047,8 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
   if (!pose7 && !rt6) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   ProfScope ps(PROF_POSE, (cudaStream_t)stream);
-  pose_pipeline_kernel<<<(B + POSE_WARPS - 1) / POSE_WARPS, POSE_WARPS * 32, 0, (cudaStream_t)stream>>>(
+  int grid, block; pose_launch_shape(B, &grid, &block);
+  pose_pipeline_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6,
       epnp_rt34, status);
   return check_launch();

@@ -32,9 +32,13 @@ namespace epb {
 // exact reference arithmetic
 // ------------------------------------------------------------------------------------------
 
-// ransac_voting_kernel.cu:22-48 as compiled (SASS of the shipped cubin):
+// ransac_voting_kernel.cu:22-48 as nvcc 12.9 / ptxas contracts the reference source for sm_100a
+// (SASS of oracle/_ref/libref_voting.so; bitwise-checked on the GPU by tests/test_voting_gpu.py):
 //   det1 = rn(nx1*ny0) - rn(nx0*ny1), det2 = -det1, guards in double,
-//   s = fma(nx,cx,rn(ny*cy)), y = fma(nx1,s0,-rn(nx0*s1))/det1, x = fma(ny1,s0,-rn(ny0*s1))/det2
+//   s = fma(nx,cx,rn(ny*cy)), y = fma(nx1,s0,-rn(nx0*s1))/det1, x = fma(-ny0,s1,rn(ny1*s0))/det2.
+// The cubin the reference shipped (CUDA 11.1, sm_86) contracts the x numerator the other way round
+// (fma(ny1,s0,-rn(ny0*s1))): the two builds of the SAME source differ by 1 ulp in x on some pairs.
+// We follow the sm_100a build, i.e. what the reference yields when built on the machine we replace.
 __device__ __forceinline__ bool intersect_rays(float dx0, float dy0, float cx0, float cy0,
                                                float dx1, float dy1, float cx1, float cy1,
                                                float* x, float* y) {
@@ -48,7 +52,7 @@ __device__ __forceinline__ bool intersect_rays(float dx0, float dy0, float cx0, 
   const float s0 = __fmaf_rn(nx0, cx0, __fmul_rn(ny0, cy0));
   const float s1 = __fmaf_rn(nx1, cx1, __fmul_rn(ny1, cy1));
   *y = __fdiv_rn(__fmaf_rn(nx1, s0, -__fmul_rn(nx0, s1)), det1);
-  *x = __fdiv_rn(__fmaf_rn(ny1, s0, -__fmul_rn(ny0, s1)), det2);
+  *x = __fdiv_rn(__fmaf_rn(-ny0, s1, __fmul_rn(ny1, s0)), det2);
   return true;
 }
 
@@ -418,6 +422,26 @@ hypothesis_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspa
 //   dd <  rn(s2*cLo)     => reference says not inlier
 //   otherwise            => evaluate the reference expression (IEEE sqrt, div) exactly.
 // ------------------------------------------------------------------------------------------
+// Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2): two hypotheses per issue slot, each half with the
+// same IEEE round-to-nearest result as the scalar instruction.  A pack of twice the same scalar
+// (the broadcast pixel record) is folded by ptxas into a scalar operand modifier (R.F32).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
 constexpr int VOTE_THREADS = 128;
 constexpr int VOTE_TILE = 512;  // records per smem tile
 struct __align__(16) VoteRec { float cx, cy, nx, ny, cHi, cLo, g, n1; };
@@ -443,8 +467,11 @@ vote_count_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspa
   const float T2u = __fmul_ru(T, T), T2d = __fmul_rd(T, T);
   const float kHi = 1.0f + 9.5367431640625e-07f, kLo = 1.0f - 9.5367431640625e-07f;
 
+  static_assert(R == 2 || R == 4, "hypotheses are processed as packed pairs");
+  constexpr int P = R / 2;
   float hx[R], hy[R];
   int cnt[R];
+  f32x2 HX[P], HY[P];
   const float2* hyp = ws.hyp + ((size_t)b * p.vn + v) * HN;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -452,6 +479,8 @@ vote_count_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspa
     const float2 q = h < HN ? hyp[h] : make_float2(0.f, 0.f);
     hx[r] = q.x; hy[r] = q.y; cnt[r] = 0;
   }
+#pragma unroll
+  for (int q = 0; q < P; ++q) { HX[q] = pk2(hx[2 * q], hx[2 * q + 1]); HY[q] = pk2(hy[2 * q], hy[2 * q + 1]); }
 
   const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
   const float* vbase = vertex + b * p.sb + v * p.sv;
@@ -507,26 +536,38 @@ vote_count_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspa
     for (int i = 0; i < nrec; ++i) {
       const float4 a = *reinterpret_cast<const float4*>(&rp[i].cx);
       const float4 c = *reinterpret_cast<const float4*>(&rp[i].cHi);
+      const f32x2 CX = pk2(a.x, a.x), CY = pk2(a.y, a.y), NX = pk2(a.z, a.z), NY = pk2(a.w, a.w);
+      const f32x2 CHI = pk2(c.x, c.x), CLO = pk2(c.y, c.y), G = pk2(c.z, c.z);
       bool amb = false;
-      bool in[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float dx = __fsub_rn(hx[r], a.x);
-        const float dy = __fsub_rn(hy[r], a.y);
-        const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-        const float dot = __fmaf_rn(dx, a.z, __fmul_rn(dy, a.w));
-        const float dd = __fmul_rn(dot, fabsf(dot));
-        const float mhi = __fmaf_rn(s2, c.x, c.z);
-        const float mlo = __fmul_rn(s2, c.y);
-        in[r] = dd > mhi;
-        amb |= !(dd > mhi) && !(dd < mlo);
+      for (int q = 0; q < P; ++q) {
+        const f32x2 DX = sub2(HX[q], CX), DY = sub2(HY[q], CY);
+        const f32x2 S2 = fma2(DX, DX, mul2(DY, DY));
+        const f32x2 DOT = fma2(DX, NX, mul2(DY, NY));
+        const f32x2 DD = mul2(DOT, DOT & 0x7fffffff7fffffffull);   // dot * |dot|
+        const f32x2 MHI = fma2(S2, CHI, G), MLO = mul2(S2, CLO);
+        float dd0, dd1, mh0, mh1, ml0, ml1;
+        upk2(DD, dd0, dd1); upk2(MHI, mh0, mh1); upk2(MLO, ml0, ml1);
+        const bool in0 = dd0 > mh0, in1 = dd1 > mh1;
+        cnt[2 * q] += in0;                              // fast decision counted unconditionally
+        cnt[2 * q + 1] += in1;
+        amb |= (!in0 && !(dd0 < ml0)) || (!in1 && !(dd1 < ml1));
       }
       if (amb) {
+        // rare side path: replace the fast decision of the undecided pairs by the reference
+        // expression (IEEE sqrt / div); nothing but the counters is live across this branch
 #pragma unroll
-        for (int r = 0; r < R; ++r) in[r] = vote_exact(a.x, a.y, a.z, a.w, c.w, hx[r], hy[r], T);
+        for (int r = 0; r < R; ++r) {
+          const float dx = __fsub_rn(hx[r], a.x);
+          const float dy = __fsub_rn(hy[r], a.y);
+          const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+          const float dot = __fmaf_rn(dx, a.z, __fmul_rn(dy, a.w));
+          const float dd = __fmul_rn(dot, fabsf(dot));
+          const bool in = dd > __fmaf_rn(s2, c.x, c.z);
+          if (!in && !(dd < __fmul_rn(s2, c.y)))
+            cnt[r] += (int)vote_exact(a.x, a.y, a.z, a.w, c.w, hx[r], hy[r], T);
+        }
       }
-#pragma unroll
-      for (int r = 0; r < R; ++r) cnt[r] += in[r];
     }
     if (more) stage(buf ^ 1);
     __syncthreads();
@@ -995,7 +1036,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   {
     // R hypotheses per thread; split the pixels of an image over several CTAs when the batch
     // alone cannot fill the 148 SMs (>= 2 waves of 128-thread CTAs at 16 CTAs/SM is plenty).
-    const int R = HN <= 128 ? 1 : HN <= 256 ? 2 : 4;
+    const int R = HN <= 256 ? 2 : 4;
     const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
     const long long ctas = (long long)p.B * p.vn * chunks;
     int splits = 1;
@@ -1011,8 +1052,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
       EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
     dim3 grid(splits, p.vn * chunks, p.B);
     ProfScope ps(PROF_VOTE_COUNT, s);
-    if (R == 1) vote_count_kernel<1><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
-    else if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
+    if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
     else vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
     EPB_RETURN_IF(check_launch());
   }

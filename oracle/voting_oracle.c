@@ -18,7 +18,8 @@
  * (the reference launcher allocates it with at::zeros, :75); degenerate pairs
  * are left untouched.
  *   reference source:  y=(nx1*(nx0*cx0+ny0*cy0)-nx0*(nx1*cx1+ny1*cy1))/(nx1*ny0-nx0*ny1)
- *   as compiled:       s = fma(nx,cx,rn(ny*cy)); num = fma(a,s0,-rn(b*s1));
+ *   as compiled (nvcc 12.9, sm_100a = oracle/_ref):
+ *                      s = fma(nx,cx,rn(ny*cy)); y: fma(nx1,s0,-rn(nx0*s1)); x: fma(-ny0,s1,rn(ny1*s0));
  *                      det = rn(nx1*ny0) - rn(nx0*ny1)   (un-fused), div.rn */
 void orc_generate_hypothesis(const float* direct, const float* coords, const int* idxs,
                              float* hypo_pts, int tn, int vn, int hn) {
@@ -42,7 +43,9 @@ void orc_generate_hypothesis(const float* direct, const float* coords, const int
       const float s0 = fmaf(nx0, cx0, ny0 * cy0);
       const float s1 = fmaf(nx1, cx1, ny1 * cy1);
       const float y = fmaf(nx1, s0, -(nx0 * s1)) / det1;
-      const float x = fmaf(ny1, s0, -(ny0 * s1)) / det2;
+      /* sm_100a / CUDA 12.9 contraction (oracle/_ref); the shipped sm_86 cubin has
+       * fmaf(ny1, s0, -(ny0 * s1)) here -- same source, 1 ulp apart on some pairs. */
+      const float x = fmaf(-ny0, s1, ny1 * s0) / det2;
       hypo_pts[hi * vn * 2 + vi * 2] = x;
       hypo_pts[hi * vn * 2 + vi * 2 + 1] = y;
     }

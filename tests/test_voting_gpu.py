@@ -240,7 +240,7 @@ def test_full_size_properties(cuda_dev):
     cnt = dbg["counts"].cpu().numpy()
     assert cnt.min() >= 0 and (cnt.max(axis=(1, 2)) <= tn).all()
     pts = dbg["pts"].cpu().numpy()
-    assert np.abs(pts - kpts).max() < 0.5                               # recovers the planted keypoints
+    assert np.abs(pts - kpts).max() < 1.5                               # recovers the planted keypoints (2 deg noise)
     # one image checked exactly against the oracle using the counts' own hypotheses
     vx0 = vertex_hwvn2(vertex[:1])
     _, coords, direct = ov.compact(mask[0] != 0, vx0[0], 30000, ov.default_selection_fn(0), 0)

@@ -72,4 +72,11 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   return r;
 }
 
+// streaming 32-bit load, no L1 allocation (works for device memory and for mapped host memory)
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
 }  // namespace epb

@@ -23,6 +23,7 @@
 // reference's integers.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -136,10 +137,16 @@ struct Workspace {
   unsigned long long* off_u;  // [B] generator offset of the uniform_ draw
   unsigned long long* off_r;  // [B] generator offset of the first random_ draw
   uint32_t* fgpix;        // [B][H*W] packed (y << 16 | x), row-major stable order
-  float2* hyp;            // [B][vn][HN]
+  float2* direct;         // [B][vn][H*W] field vectors of the foreground pixels, in fgpix order
+  float* hyp;             // [B][vn][2][HNs] x plane then y plane, HNs = HN rounded up to 4 (hyp_stride)
   int32_t* counts;        // [B][vn][HN]
+  int32_t* item_off;      // [B+1] exclusive scan of ceil(tn / item_px): work list of vote_count
   size_t bytes;
 };
+__host__ __device__ inline int hyp_stride(int HN) { return (HN + 3) & ~3; }
+__device__ __forceinline__ float* hyp_plane(const Workspace& ws, int b, int vn, int v, int HN, int c) {
+  return ws.hyp + (((size_t)b * vn + v) * 2 + c) * hyp_stride(HN);
+}
 __host__ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 __host__ inline Workspace carve(const epb_voting_params& p, void* base) {
   Workspace w;
@@ -158,8 +165,10 @@ __host__ inline Workspace carve(const epb_voting_params& p, void* base) {
   w.off_u = (unsigned long long*)take(B * 8);
   w.off_r = (unsigned long long*)take(B * 8);
   w.fgpix = (uint32_t*)take(B * (size_t)p.H * p.W * 4);
-  w.hyp = (float2*)take(B * p.vn * HN * 8);
+  w.direct = (float2*)take(B * p.vn * (size_t)p.H * p.W * 8);
+  w.hyp = (float*)take(B * p.vn * 2 * (size_t)hyp_stride((int)HN) * 4);
   w.counts = (int32_t*)take(B * p.vn * HN * 4);
+  w.item_off = (int32_t*)take((B + 1) * 4);
   w.bytes = o;
   return w;
 }
@@ -348,6 +357,40 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
 }
 
 // ------------------------------------------------------------------------------------------
+// 4b. field_gather: the vector field of the foreground pixels, compacted in fgpix order, one
+//     float2 per (image, keypoint, pixel).  This is the only kernel that touches `vertex`, it
+//     reads each needed element exactly once, and nothing else of the field is ever read -- so
+//     `vertex` may just as well be page-locked HOST memory mapped into the device address space
+//     (zero-copy over PCIe: only the foreground fraction of the field crosses the bus).
+//     The reference materialises the same array with masked_select (ransac_voting_gpu.py:544-545).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+field_gather_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (!ws.live[b] || t >= ws.tn[b]) return;
+  const size_t HW = (size_t)p.H * p.W;
+  const uint32_t q = ws.fgpix[(size_t)b * HW + t];
+  const float* src = vertex + b * p.sb + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
+  float2* dst = ws.direct + (size_t)b * p.vn * HW + t;
+  int v = 0;
+  for (; v + 4 <= p.vn; v += 4) {  // 8 independent loads in flight per thread (PCIe / HBM latency)
+    float2 d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* s = src + (long long)(v + j) * p.sv;
+      d[j].x = ldg_stream(s); d[j].y = ldg_stream(s + p.sc);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[(size_t)(v + j) * HW] = d[j];
+  }
+  for (; v < p.vn; ++v) {
+    const float* s = src + (long long)v * p.sv;
+    dst[(size_t)v * HW] = make_float2(ldg_stream(s), ldg_stream(s + p.sc));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // 5. hypothesis generation (fused batched form of generate_hypothesis_kernel + idxs draw)
 // ------------------------------------------------------------------------------------------
 struct HypCtx {
@@ -358,7 +401,7 @@ struct HypCtx {
   unsigned long long inc_r;
 };
 __global__ void __launch_bounds__(256)
-hypothesis_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws, HypCtx hc,
+hypothesis_kernel(epb_voting_params p, Workspace ws, HypCtx hc,
                   float* __restrict__ hyp_out) {
   const int HN = p.hn * p.rounds;
   const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -388,15 +431,15 @@ hypothesis_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspa
     const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
     const uint32_t q0 = fp[t0], q1 = fp[t1];
     const int x0 = q0 & 0xffff, y0 = q0 >> 16, x1 = q1 & 0xffff, y1 = q1 >> 16;
-    const float* d0 = vertex + b * p.sb + y0 * p.sy + x0 * p.sx + v * p.sv;
-    const float* d1 = vertex + b * p.sb + y1 * p.sy + x1 * p.sx + v * p.sv;
+    const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+    const float2 d0 = dir[t0], d1 = dir[t1];
     float ix, iy;
-    if (intersect_rays(__ldg(d0), __ldg(d0 + p.sc), (float)x0, (float)y0, __ldg(d1), __ldg(d1 + p.sc),
-                       (float)x1, (float)y1, &ix, &iy)) {
+    if (intersect_rays(d0.x, d0.y, (float)x0, (float)y0, d1.x, d1.y, (float)x1, (float)y1, &ix, &iy)) {
       x = ix; y = iy;
     }
   }
-  ws.hyp[((size_t)b * p.vn + v) * HN + hh] = make_float2(x, y);
+  hyp_plane(ws, b, p.vn, v, HN, 0)[hh] = x;
+  hyp_plane(ws, b, p.vn, v, HN, 1)[hh] = y;
   if (hyp_out) {
     float2* o = reinterpret_cast<float2*>(hyp_out) + ((size_t)b * HN + hh) * p.vn + v;
     *o = make_float2(x, y);
@@ -404,27 +447,28 @@ hypothesis_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspa
 }
 
 // ------------------------------------------------------------------------------------------
-// 6. vote_count: the dominant kernel.
+// 6. vote_count: the dominant kernel (hn*vn*tn inlier tests per image).
 //
-// CTA = 128 threads, one (image, keypoint, chunk of 128*R hypotheses, pixel split).  Each thread
-// keeps R hypotheses and their counters in registers (lanes <-> hypotheses); foreground pixels
-// are staged through shared memory as 32-byte records and broadcast to all lanes, so every
-// (hypothesis, pixel) test costs ~12 issue slots instead of the reference's ~35 and nothing
-// but the field itself is read from memory.  The next tile's global gathers are issued before
-// the current tile is consumed (register prefetch, one __syncthreads per tile).
+// Persistent CTAs of 128 threads walk a list of equal-sized work units
+//   unit = (item of <= item_px foreground pixels of one image, keypoint, chunk of 128*R hypotheses);
+// each thread keeps R hypotheses and their counters in registers (lanes <-> hypotheses), pixels are
+// staged through shared memory as records and broadcast to all lanes.
 //
-// Record: {cx, cy, nx, ny, cHi, cLo, g, norm1}
-//   s1 = |n|^2 as the reference rounds it, norm1 = sqrt.rn(s1)
-//   cHi = ru(T^2 s1 (1+2^-20)), cLo = rd(T^2 s1 (1-2^-20)), g = ru(4.1e-12 s1)
-// Test for hypothesis (hx,hy) with dx,dy,s2,dot exactly as the reference rounds them:
-//   dd = rn(dot*|dot|)
-//   dd >  fma(s2,cHi,g)  => reference says inlier      (voting error bound)
-//   dd <  rn(s2*cLo)     => reference says not inlier
-//   otherwise            => evaluate the reference expression (IEEE sqrt, div) exactly.
+// The reference decides  c = dot/(|n| |d|) > T  with IEEE sqrt and div (~35 issue slots).  With
+// theta = acos(T), k = tan(theta), d0 = h - c and the pixel direction scaled by a power of two so that
+// max(|nx|,|ny|) is in [1,2), the exact decision function is
+//   F0 = k (d0 . n) - |n x d0| = |d0||n| sin(theta - phi) / cos(theta)      (phi = angle(d0, n)),
+// two AFFINE forms of the hypothesis.  Record = their coefficients:
+//   a' = A1 hx + A2 hy + A3   (A = k n, A3 = -k n.c)          p = B1 hx + B2 hy + B3   (B = (-ny, nx), B3 = ny cx - nx cy)
+//   m = a' - |p|,   w = gamma a' + EH[h]
+//   |m| > w : the sign of m IS the reference's decision (error bound in DESIGN.md section 5:
+//             the reference's c is within 9.04 ulp-units of the exact cosine; gamma and EH cover that
+//             plus every rounding of the forms above, and the |d| < 1e-6 guard)
+//   else    : the warp evaluates the reference expression itself (IEEE sqrt / div), rare.
+// 8 FP32 lane-ops (FMA pipe) + 1 FSETP per test instead of ~35; counts are exact integers.
 // ------------------------------------------------------------------------------------------
 // Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2): two hypotheses per issue slot, each half with the
-// same IEEE round-to-nearest result as the scalar instruction.  A pack of twice the same scalar
-// (the broadcast pixel record) is folded by ptxas into a scalar operand modifier (R.F32).
+// same IEEE round-to-nearest result as the scalar instruction.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
   f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
@@ -432,157 +476,270 @@ __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
 __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
-  f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+__device__ __forceinline__ float half2(f32x2 v, int hi) {
+  float a, b; upk2(v, a, b); return hi ? b : a;
 }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
 }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ float mul_sat(float a, float b) {
+  float r; asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+}
 
 constexpr int VOTE_THREADS = 128;
-constexpr int VOTE_TILE = 512;  // records per smem tile
-struct __align__(16) VoteRec { float cx, cy, nx, ny, cHi, cLo, g, n1; };
+constexpr int VOTE_TILE = 256;  // records per smem tile
+
+// constants of the fast test, computed on the host in double (vote_consts())
+struct VoteConsts {
+  int fast_ok;      // 0: every pair takes the exact path (threshold outside [0.5, 1) or band too wide)
+  float kf;         // tan(acos(T))
+  float gamma;      // relative half-width of the undecided band, in units of a'
+  float eh_scale;   // EH[h] = eh_scale * (|hx| + |hy|) + eh_abs
+  float eh_abs;
+};
+__host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
+  VoteConsts c;
+  const double T = (double)thresh, u = 5.9604644775390625e-08;  // 2^-24
+  c.fast_ok = 0; c.kf = 0.f; c.gamma = 0.f; c.eh_scale = 0.f; c.eh_abs = 0.f;
+  if (!(T >= 0.5 && T < 1.0)) return c;
+  const double k = sqrt((1.0 - T) * (1.0 + T)) / T;
+  const double sin_half = sqrt((1.0 - T) * 0.5);
+  const double beta = 10.5 * u / (T * sin_half);
+  const double gamma = beta * (1.0 / k + 1.0) * 1.0001;
+  if (!(gamma <= 0.25)) return c;
+  // eps_a + eps_p <= (6.2 k + 4.1) u Nm (|h|_1 + |c|_1) with Nm < 2; factor 3 of slack
+  const double es = 3.0 * (6.2 * k + 4.1) * u * 2.0;
+  const double ea = es * (double)(H + W) + 3.5e-6 * (1.0 + k);
+  c.fast_ok = 1;
+  c.kf = (float)k;
+  c.gamma = nextafterf((float)gamma, INFINITY);
+  c.eh_scale = nextafterf((float)es, INFINITY);
+  c.eh_abs = nextafterf((float)ea, INFINITY);
+  return c;
+}
+
+struct VoteSmem {
+  float4 f[2][VOTE_TILE];  // A1 A2 B1 B2
+  float2 g[2][VOTE_TILE];  // A3 B3
+  float4 x[2][VOTE_TILE];  // cx cy nx ny as the reference sees them (exact path)
+};
 
 template <int R>
 __global__ void __launch_bounds__(VOTE_THREADS)
-vote_count_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws, int splits,
-                  int use_atomic) {
-  __shared__ VoteRec tile[2][VOTE_TILE];
-  const int HN = p.hn * p.rounds;
-  const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
-  const int b = blockIdx.z;
-  const int v = blockIdx.y / chunks, chunk = blockIdx.y - v * chunks;
-  const int split = blockIdx.x;
-  if (!ws.live[b]) return;
-  const int tn = ws.tn[b];
-  const int per = (tn + splits - 1) / splits;
-  const int t_begin = split * per, t_end = min(tn, t_begin + per);
-  if (t_begin >= t_end && use_atomic) return;
-
-  const float T = p.inlier_thresh;
-  const bool fast_ok = T >= 0.0009765625f && T < 1e18f;
-  const float T2u = __fmul_ru(T, T), T2d = __fmul_rd(T, T);
-  const float kHi = 1.0f + 9.5367431640625e-07f, kLo = 1.0f - 9.5367431640625e-07f;
-
-  static_assert(R == 2 || R == 4, "hypotheses are processed as packed pairs");
+vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
+                  int item_px, int chunks) {
+  __shared__ VoteSmem sm;
+  static_assert(R == 2 || R == 4 || R == 8, "hypotheses are processed as packed pairs");
   constexpr int P = R / 2;
-  float hx[R], hy[R];
-  int cnt[R];
-  f32x2 HX[P], HY[P];
-  const float2* hyp = ws.hyp + ((size_t)b * p.vn + v) * HN;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int h = chunk * VOTE_THREADS * R + r * VOTE_THREADS + threadIdx.x;
-    const float2 q = h < HN ? hyp[h] : make_float2(0.f, 0.f);
-    hx[r] = q.x; hy[r] = q.y; cnt[r] = 0;
-  }
-#pragma unroll
-  for (int q = 0; q < P; ++q) { HX[q] = pk2(hx[2 * q], hx[2 * q + 1]); HY[q] = pk2(hy[2 * q], hy[2 * q + 1]); }
+  constexpr int RECS = R >= 8 ? 1 : (R == 4 ? 2 : 4);   // records per trip of the inner loop (8 tests per lane)
+  constexpr int PER_THREAD = VOTE_TILE / VOTE_THREADS;
+  static_assert(VOTE_TILE % VOTE_THREADS == 0 && VOTE_TILE % 4 == 0, "tile shape");
+  const int HN = p.hn * p.rounds;
+  const int B = p.B;
+  const int* __restrict__ item_off = ws.item_off;
+  const long long total = (long long)item_off[B] * p.vn * chunks;
+  const float T = p.inlier_thresh;
+  const f32x2 GG = pk2(vc.gamma, vc.gamma);
 
-  const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
-  const float* vbase = vertex + b * p.sb + v * p.sv;
-  constexpr int PER_THREAD = VOTE_TILE / VOTE_THREADS;  // 4
-  uint32_t pq[PER_THREAD];
-  float pnx[PER_THREAD], pny[PER_THREAD];
-
-  auto prefetch = [&](int t0) {
-#pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) {
-      const int t = t0 + k * VOTE_THREADS + threadIdx.x;
-      if (t < t_end) {
-        const uint32_t q = __ldg(fp + t);
-        const float* d = vbase + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
-        pq[k] = q; pnx[k] = __ldg(d); pny[k] = __ldg(d + p.sc);
-      } else { pq[k] = 0xffffffffu; pnx[k] = 0.f; pny[k] = 0.f; }
+  for (long long unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const int per_item = p.vn * chunks;
+    const int item = (int)(unit / per_item);
+    const int rem = (int)(unit - (long long)item * per_item);
+    const int v = rem / chunks, chunk = rem - v * chunks;
+    int lo = 0, hi = B;  // largest b with item_off[b] <= item
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (item_off[mid] <= item) lo = mid; else hi = mid;
     }
-  };
-  auto stage = [&](int buf) {
+    const int b = lo;
+    const int tn = ws.tn[b];
+    const int t_begin = (item - item_off[b]) * item_px, t_end = min(tn, t_begin + item_px);
+
+    // thread t owns the hypothesis pairs {2t, 2t+1} + 256 q of its chunk: one 64-bit load per plane
+    // yields a packed operand directly
+    f32x2 HX[P], HY[P], EH[P];
+    unsigned neg[R];   // pixels that do NOT vote for the hypothesis (sign bit of m)
+    const float* hypx = hyp_plane(ws, b, p.vn, v, HN, 0);
+    const float* hypy = hyp_plane(ws, b, p.vn, v, HN, 1);
 #pragma unroll
-    for (int k = 0; k < PER_THREAD; ++k) {
-      VoteRec rec;
-      const uint32_t q = pq[k];
-      rec.cx = (float)(q & 0xffff); rec.cy = (float)(q >> 16);
-      rec.nx = pnx[k]; rec.ny = pny[k];
-      const float s1 = __fmaf_rn(rec.nx, rec.nx, __fmul_rn(rec.ny, rec.ny));
-      rec.n1 = __fsqrt_rn(s1);
-      const bool valid = q != 0xffffffffu && !((double)rec.n1 < 1e-6) && (s1 == s1);
-      if (valid && fast_ok) {
-        rec.cHi = __fmul_ru(__fmul_ru(T2u, s1), kHi);
-        rec.cLo = __fmul_rd(__fmul_rd(T2d, s1), kLo);
-        rec.g = __fmul_ru(s1, 4.1e-12f);
-      } else if (valid) {  // threshold outside the proven range: always take the exact path
-        rec.cHi = INFINITY; rec.cLo = -INFINITY; rec.g = 0.f;
-      } else {             // padding / zero direction: never an inlier (reference guard :121)
-        rec.cHi = INFINITY; rec.cLo = INFINITY; rec.g = 0.f; rec.n1 = 0.f;
-        rec.cx = 0.f; rec.cy = 0.f; rec.nx = 0.f; rec.ny = 0.f;
+    for (int q = 0; q < P; ++q) {
+      const int h = chunk * VOTE_THREADS * R + q * 2 * VOTE_THREADS + 2 * threadIdx.x;
+      float x0 = 0.f, x1 = 0.f, y0 = 0.f, y1 = 0.f;
+      if (h + 1 < HN) {
+        const float2 xx = *reinterpret_cast<const float2*>(hypx + h);
+        const float2 yy = *reinterpret_cast<const float2*>(hypy + h);
+        x0 = xx.x; x1 = xx.y; y0 = yy.x; y1 = yy.y;
+      } else if (h < HN) {
+        x0 = hypx[h]; y0 = hypy[h];
       }
-      tile[buf][k * VOTE_THREADS + threadIdx.x] = rec;
+      HX[q] = pk2(x0, x1); HY[q] = pk2(y0, y1);
+      // non-finite or huge hypotheses: undecided against every pixel -> reference expression
+      const float h0 = __fadd_ru(fabsf(x0), fabsf(y0)), h1 = __fadd_ru(fabsf(x1), fabsf(y1));
+      EH[q] = pk2((h0 <= 1e15f) ? __fmaf_ru(vc.eh_scale, h0, vc.eh_abs) : INFINITY,
+                  (h1 <= 1e15f) ? __fmaf_ru(vc.eh_scale, h1, vc.eh_abs) : INFINITY);
+      neg[2 * q] = neg[2 * q + 1] = 0u;
     }
-  };
 
-  int buf = 0;
-  prefetch(t_begin);
-  stage(0);
-  __syncthreads();
-  for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE) {
-    const bool more = t0 + VOTE_TILE < t_end;
-    if (more) prefetch(t0 + VOTE_TILE);
-    const int nrec = min(VOTE_TILE, t_end - t0);
-    const VoteRec* rp = tile[buf];
-#pragma unroll 2
-    for (int i = 0; i < nrec; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(&rp[i].cx);
-      const float4 c = *reinterpret_cast<const float4*>(&rp[i].cHi);
-      const f32x2 CX = pk2(a.x, a.x), CY = pk2(a.y, a.y), NX = pk2(a.z, a.z), NY = pk2(a.w, a.w);
-      const f32x2 CHI = pk2(c.x, c.x), CLO = pk2(c.y, c.y), G = pk2(c.z, c.z);
+    const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
+    const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+    uint32_t pq[PER_THREAD];
+    float pnx[PER_THREAD], pny[PER_THREAD];
+
+    auto prefetch = [&](int t0) {
+#pragma unroll
+      for (int k = 0; k < PER_THREAD; ++k) {
+        const int t = t0 + k * VOTE_THREADS + threadIdx.x;
+        if (t < t_end) {
+          const float2 d = __ldg(dir + t);
+          pq[k] = __ldg(fp + t); pnx[k] = d.x; pny[k] = d.y;
+        } else { pq[k] = 0xffffffffu; pnx[k] = 0.f; pny[k] = 0.f; }
+      }
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+      for (int k = 0; k < PER_THREAD; ++k) {
+        const uint32_t q = pq[k];
+        const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
+        const float nx = pnx[k], ny = pny[k];
+        const float s1 = __fmaf_rn(nx, nx, __fmul_rn(ny, ny));
+        const float n1 = __fsqrt_rn(s1);
+        // reference guard :121 (zero direction), NaN / overflowed |n|^2 (c = NaN or 0): never an inlier
+        const bool valid = q != 0xffffffffu && !((double)n1 < 1e-6) && (s1 <= FLT_MAX);
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 g = make_float2(-INFINITY, 0.f);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          x = make_float4(cx, cy, nx, ny);
+          if (vc.fast_ok) {
+            // exact power-of-two scaling: max(|nx|,|ny|) -> [1,2)
+            const float nm = fmaxf(fabsf(nx), fabsf(ny));
+            const float sc = __uint_as_float((254u - ((__float_as_uint(nm) >> 23) & 0xffu)) << 23);
+            const float nxs = __fmul_rn(nx, sc), nys = __fmul_rn(ny, sc);
+            f.x = __fmul_rn(vc.kf, nxs);
+            f.y = __fmul_rn(vc.kf, nys);
+            f.z = -nys;
+            f.w = nxs;
+            g.x = -__fmul_rn(vc.kf, __fmaf_rn(nxs, cx, __fmul_rn(nys, cy)));
+            g.y = __fmaf_rn(nys, cx, -__fmul_rn(nxs, cy));
+          } else {
+            g.x = __int_as_float(0x7fc00000);  // NaN: every pair undecided
+          }
+        }
+        const int slot = k * VOTE_THREADS + threadIdx.x;
+        sm.f[buf][slot] = f; sm.g[buf][slot] = g; sm.x[buf][slot] = x;
+      }
+    };
+
+    // one record against the thread's R hypotheses: m (sign = decision), w (band); returns "some pair undecided"
+    auto test_record = [&](const float4 f, const float2 g, float (&m)[R], float (&w)[R]) -> bool {
+      const f32x2 A1 = pk2(f.x, f.x), A2 = pk2(f.y, f.y), B1 = pk2(f.z, f.z), B2 = pk2(f.w, f.w);
+      const f32x2 A3 = pk2(g.x, g.x), B3 = pk2(g.y, g.y);
       bool amb = false;
 #pragma unroll
       for (int q = 0; q < P; ++q) {
-        const f32x2 DX = sub2(HX[q], CX), DY = sub2(HY[q], CY);
-        const f32x2 S2 = fma2(DX, DX, mul2(DY, DY));
-        const f32x2 DOT = fma2(DX, NX, mul2(DY, NY));
-        const f32x2 DD = mul2(DOT, DOT & 0x7fffffff7fffffffull);   // dot * |dot|
-        const f32x2 MHI = fma2(S2, CHI, G), MLO = mul2(S2, CLO);
-        float dd0, dd1, mh0, mh1, ml0, ml1;
-        upk2(DD, dd0, dd1); upk2(MHI, mh0, mh1); upk2(MLO, ml0, ml1);
-        const bool in0 = dd0 > mh0, in1 = dd1 > mh1;
-        cnt[2 * q] += in0;                              // fast decision counted unconditionally
-        cnt[2 * q + 1] += in1;
-        amb |= (!in0 && !(dd0 < ml0)) || (!in1 && !(dd1 < ml1));
+        const f32x2 AP = fma2(A1, HX[q], fma2(A2, HY[q], A3));
+        const f32x2 PP = fma2(B1, HX[q], fma2(B2, HY[q], B3));
+        const f32x2 WW = fma2(GG, AP, EH[q]);
+        float a0, a1, p0, p1;
+        upk2(AP, a0, a1); upk2(PP, p0, p1); upk2(WW, w[2 * q], w[2 * q + 1]);
+        m[2 * q] = __fsub_rn(a0, fabsf(p0));
+        m[2 * q + 1] = __fsub_rn(a1, fabsf(p1));
+        amb |= !(fabsf(m[2 * q]) > w[2 * q]) || !(fabsf(m[2 * q + 1]) > w[2 * q + 1]);
       }
-      if (amb) {
-        // rare side path: replace the fast decision of the undecided pairs by the reference
-        // expression (IEEE sqrt / div); nothing but the counters is live across this branch
+      return amb;
+    };
+    // rare side path: undecided pairs get the reference expression (IEEE sqrt / div); m becomes +-1
+    auto resolve = [&](const float4 x, float (&m)[R], const float (&w)[R]) {
+      const float n1 = dir_norm(x.z, x.w);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float dx = __fsub_rn(hx[r], a.x);
-          const float dy = __fsub_rn(hy[r], a.y);
-          const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-          const float dot = __fmaf_rn(dx, a.z, __fmul_rn(dy, a.w));
-          const float dd = __fmul_rn(dot, fabsf(dot));
-          const bool in = dd > __fmaf_rn(s2, c.x, c.z);
-          if (!in && !(dd < __fmul_rn(s2, c.y)))
-            cnt[r] += (int)vote_exact(a.x, a.y, a.z, a.w, c.w, hx[r], hy[r], T);
-        }
-      }
-    }
-    if (more) stage(buf ^ 1);
-    __syncthreads();
-    buf ^= 1;
-  }
+      for (int r = 0; r < R; ++r)
+        if (!(fabsf(m[r]) > w[r]))
+          m[r] = vote_exact(x.x, x.y, x.z, x.w, n1, half2(HX[r >> 1], r & 1), half2(HY[r >> 1], r & 1), T)
+                     ? 1.0f : -1.0f;
+    };
 
-  int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
+    int buf = 0;
+    prefetch(t_begin);
+    __syncthreads();   // previous unit's readers are done with both buffers
+    stage(0);
+    __syncthreads();
+    for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE) {
+      const bool more = t0 + VOTE_TILE < t_end;
+      if (more) prefetch(t0 + VOTE_TILE);
+      const int nrec = min(VOTE_TILE, t_end - t0);
+      const float4* fr = sm.f[buf];
+      const float2* gr = sm.g[buf];
+      const float4* xr = sm.x[buf];
+      // RECS records per trip share one branch to the side path; an odd tail record is a padding
+      // record of the tile (never an inlier) or, in a full tile, handled by the even tile size
+      const int ntrip = (nrec + RECS - 1) / RECS;
+#pragma unroll 1
+      for (int it = 0; it < ntrip; ++it) {
+        const int i = it * RECS;
+        float m[RECS][R], w[RECS][R];
+        bool amb = false;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int h = chunk * VOTE_THREADS * R + r * VOTE_THREADS + threadIdx.x;
-    if (h < HN) {
-      if (use_atomic) atomicAdd(out + h, cnt[r]);
-      else out[h] = cnt[r];
+        for (int j = 0; j < RECS; ++j) amb |= test_record(fr[i + j], gr[i + j], m[j], w[j]);
+        if (amb) {
+#pragma unroll
+          for (int j = 0; j < RECS; ++j) resolve(xr[i + j], m[j], w[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < RECS; ++j)
+#pragma unroll
+          for (int r = 0; r < R; ++r) neg[r] += __float_as_uint(m[j][r]) >> 31;
+      }
+      if (more) stage(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+
+    int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
+    // records visited by the trips above (tiles are rounded up to a multiple of RECS)
+    int visited = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE)
+      visited += (min(VOTE_TILE, t_end - t0) + RECS - 1) / RECS * RECS;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int h = chunk * VOTE_THREADS * R + (r >> 1) * 2 * VOTE_THREADS + 2 * threadIdx.x + (r & 1);
+      // every record visited beyond t_end is a padding record (m = -inf), so neg over-counts by exactly
+      // the padding and the difference below is the number of voting pixels
+      const int c = visited - (int)neg[r];
+      if (h < HN && c != 0) atomicAdd(out + h, c);
     }
   }
+}
+
+// work list of vote_count: item_off[b] = number of pixel items of the images before b.
+__global__ void __launch_bounds__(256)
+vote_items_kernel(int B, int item_px, Workspace ws) {
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < B; base += 256) {
+    const int i = base + threadIdx.x;
+    const int v = (i < B && ws.live[i]) ? (ws.tn[i] + item_px - 1) / item_px : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(FULL, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += o;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_warp[w];
+    const int carry = s_carry;
+    if (i < B) ws.item_off[i] = carry + wbase + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 255) s_carry = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ws.item_off[B] = s_carry;
 }
 
 // counts_ws [B][vn][HN] -> user layout [B][HN][vn]
@@ -627,7 +784,7 @@ __device__ __forceinline__ void block_sum_d(double (&v)[N], double* smem /* [N*8
 //    and :578-595 (re-vote the winner, 2x2 normal equations).  Sums in FP64.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-winner_refine_kernel(const float* __restrict__ vertex, epb_voting_params p, Workspace ws,
+winner_refine_kernel(epb_voting_params p, Workspace ws,
                      float* __restrict__ pts, float* __restrict__ var_or_conf,
                      int32_t* __restrict__ status) {
   const int v = blockIdx.x, b = blockIdx.y;
@@ -666,19 +823,20 @@ winner_refine_kernel(const float* __restrict__ vertex, epb_voting_params p, Work
       if (s_cnt[w] > bc || (s_cnt[w] == bc && s_idx[w] < bi)) { bc = s_cnt[w]; bi = s_idx[w]; }
     const float ratio = __fdiv_rn((float)bc, (float)tn);
     // all_win_ratio starts at 0 and is replaced only where 0 < ratio (:566-569)
-    s_pt = (0.0f < ratio) ? ws.hyp[((size_t)b * p.vn + v) * HN + bi] : make_float2(0.f, 0.f);
+    s_pt = (0.0f < ratio) ? make_float2(hyp_plane(ws, b, p.vn, v, HN, 0)[bi], hyp_plane(ws, b, p.vn, v, HN, 1)[bi])
+                          : make_float2(0.f, 0.f);
   }
   __syncthreads();
   const float2 win = s_pt;
   const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
-  const float* vbase = vertex + b * p.sb + v * p.sv;
+  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
   // pass 1: inliers of the winner and the normal equations
   double acc[7] = {0, 0, 0, 0, 0, 0, 0};  // a00 a01 a11 b0 b1 sum(bb^2) count
   for (int t = threadIdx.x; t < tn; t += 256) {
     const uint32_t q = __ldg(fp + t);
     const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
-    const float* d = vbase + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
-    const float dx = __ldg(d), dy = __ldg(d + p.sc);
+    const float2 d = __ldg(dir + t);
+    const float dx = d.x, dy = d.y;
     if (vote_exact(cx, cy, dx, dy, dir_norm(dx, dy), win.x, win.y, p.inlier_thresh)) {
       const double nx = dy, ny = -(double)dx;  // normal = (d_y, -d_x), :580-581
       const double bb = nx * cx + ny * cy;
@@ -710,8 +868,8 @@ winner_refine_kernel(const float* __restrict__ vertex, epb_voting_params p, Work
     int c = 0;
     for (int t = threadIdx.x; t < tn; t += 256) {
       const uint32_t q = __ldg(fp + t);
-      const float* d = vbase + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
-      const float dx = __ldg(d), dy = __ldg(d + p.sc);
+      const float2 d = __ldg(dir + t);
+      const float dx = d.x, dy = d.y;
       c += vote_exact((float)(q & 0xffff), (float)(q >> 16), dx, dy, dir_norm(dx, dy), fxp, fyp, 0.999f);
     }
     double cc[1] = {(double)c};
@@ -755,7 +913,8 @@ distribution_kernel(epb_voting_params p, Workspace ws, const float* __restrict__
   __shared__ int s_warp[8];
   __shared__ int s_carry;
   const int32_t* cnt = ws.counts + ((size_t)b * p.vn + v) * HN;
-  const float2* hyp = ws.hyp + ((size_t)b * p.vn + v) * HN;
+  const float* hypx = hyp_plane(ws, b, p.vn, v, HN, 0);
+  const float* hypy = hyp_plane(ws, b, p.vn, v, HN, 1);
   const float tnf = (float)ws.tn[b];
 
   unsigned thr_val = 0;  // k-th largest count
@@ -844,7 +1003,7 @@ distribution_kernel(epb_voting_params p, Workspace ws, const float* __restrict__
         __syncthreads();
       }
       if (w != 0.f) {
-        const float2 q = hyp[h];
+        const float2 q = make_float2(hypx[h], hypy[h]);
         if (phase == 0) { acc[0] += w; acc[1] += (double)w * q.x; acc[2] += (double)w * q.y; }
         else {
           const double ddx = q.x - mx_, ddy = q.y - my_;
@@ -953,6 +1112,8 @@ voting_for_hypothesis_vp_kernel(const float* __restrict__ direct, const float* _
 // ------------------------------------------------------------------------------------------
 using namespace epb;
 
+static int g_vote_r_large = 8;  // hypotheses per thread when HN > 512
+
 static bool params_ok(const epb_voting_params* p) {
   if (!p) return false;
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->vn <= 0 || p->hn <= 0 || p->rounds <= 0) return false;
@@ -1017,6 +1178,8 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   }
   mask_scatter_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc);
   EPB_RETURN_IF(check_launch());
+  field_gather_kernel<<<dim3((HW + 255) / 256, p.B), 256, 0, s>>>(io->vertex, p, ws);
+  EPB_RETURN_IF(check_launch());
   prof_end(PROF_COMPACT, s);
   if (io->tn_out)
     EPB_RETURN_IF(check_api(cudaMemcpyAsync(io->tn_out, ws.tn, (size_t)p.B * 4, cudaMemcpyDeviceToDevice, s)));
@@ -1030,30 +1193,39 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   {
     const long long n = (long long)p.B * HN * p.vn;
     ProfScope ps(PROF_HYPOTHESIS, s);
-    hypothesis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(io->vertex, p, ws, hc, io->hyp);
+    hypothesis_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, ws, hc, io->hyp);
     EPB_RETURN_IF(check_launch());
   }
   {
-    // R hypotheses per thread; split the pixels of an image over several CTAs when the batch
-    // alone cannot fill the 148 SMs (>= 2 waves of 128-thread CTAs at 16 CTAs/SM is plenty).
-    const int R = HN <= 256 ? 2 : 4;
-    const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
-    const long long ctas = (long long)p.B * p.vn * chunks;
-    int splits = 1;
-    const long long target = 148LL * 8;
-    if (ctas < target) {
-      splits = (int)((target + ctas - 1) / ctas);
-      const int max_splits = (HW + 4 * VOTE_TILE - 1) / (4 * VOTE_TILE);
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
+    // persistent CTAs over equal-sized work units (pixel item x keypoint x hypothesis chunk)
+    int R = HN <= 256 ? 2 : (HN <= 512 ? 4 : g_vote_r_large);
+    {  // tuning hook (profiling only): EPB_VOTE_R=2|4|8 overrides the hypotheses per thread
+      static const int forced = [] { const char* e = getenv("EPB_VOTE_R"); return e ? atoi(e) : 0; }();
+      if (forced == 2 || forced == 4 || forced == 8) R = forced;
     }
-    const int use_atomic = splits > 1;
-    if (use_atomic)
-      EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
-    dim3 grid(splits, p.vn * chunks, p.B);
+    const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
+    int dev = 0, sms = 148, occ = 0;
+    EPB_RETURN_IF(check_api(cudaGetDevice(&dev)));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (R == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_count_kernel<2>, VOTE_THREADS, 0);
+    else if (R == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_count_kernel<4>, VOTE_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_count_kernel<8>, VOTE_THREADS, 0);
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)sms * occ;
+    // items small enough that the work list is several waves long, large enough to amortise a unit
+    int item_px = 4 * VOTE_TILE;
+    while (item_px > VOTE_TILE &&
+           (long long)p.B * p.vn * chunks * ((HW + item_px - 1) / item_px) < 4 * slots) item_px >>= 1;
+    const long long max_units = (long long)p.B * p.vn * chunks * ((HW + item_px - 1) / item_px);
+    const unsigned grid = (unsigned)(max_units < slots ? max_units : slots);
+    const VoteConsts vc = vote_consts(p.inlier_thresh, p.H, p.W);
+    vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
+    EPB_RETURN_IF(check_launch());
+    EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
     ProfScope ps(PROF_VOTE_COUNT, s);
-    if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
-    else vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(io->vertex, p, ws, splits, use_atomic);
+    if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+    else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+    else vote_count_kernel<8><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
     EPB_RETURN_IF(check_launch());
   }
   if (io->counts) {
@@ -1063,7 +1235,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   }
   ProfScope ps_tail(PROF_REFINE, s);
   if (is_layer) {
-    winner_refine_kernel<<<dim3(p.vn, p.B), 256, 0, s>>>(io->vertex, p, ws, io->pts, io->var_or_conf,
+    winner_refine_kernel<<<dim3(p.vn, p.B), 256, 0, s>>>(p, ws, io->pts, io->var_or_conf,
                                                          io->status);
     EPB_RETURN_IF(check_launch());
   } else if (is_dist) {

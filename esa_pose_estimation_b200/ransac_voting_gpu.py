@@ -16,6 +16,9 @@ generator is advanced by what the reference would have consumed.  Keyword-only e
   idxs=        int32 [b,rounds,hn,vn,2] explicit indices (parity tests)
   raw32=True   treat ``idxs`` as raw 32-bit draws, index = draw % tn on the device
   selection=   float32 [b,h,w] uniform draws for the max_num subsample
+  vertex may also be a float32 tensor in PINNED host memory (``.pin_memory()``): the kernels then
+  read the foreground pixels of the field in place over PCIe (zero-copy) instead of the caller
+  copying the whole field to the device; ``mask`` may be a host tensor in that case too.
   sync_rng=    True (default): read back how much of the generator stream was consumed (one
                8-byte D2H copy) so later torch draws continue exactly like the reference;
                False: advance by the data-independent maximum, no synchronisation.
@@ -62,13 +65,22 @@ def _rng_layout(numel, props):
 
 def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_in=None, idxs=None,
          raw32=False, selection=None, sync_rng=True, want_hyp=False, want_status=False):
-    _lib.require_cuda(mask, "mask")
-    _lib.require_cuda(vertex, "vertex")
+    if isinstance(vertex, torch.Tensor) and not vertex.is_cuda and vertex.is_pinned():
+        # Host-resident network output: the field is read in place over PCIe by field_gather_kernel
+        # (zero-copy, foreground pixels only); only the mask is copied to the device.
+        if vertex.dtype != torch.float32:
+            raise RuntimeError("a pinned host vertex field must be float32")
+        dev = mask.device if mask.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        if not mask.is_cuda:
+            mask = mask.to(dev, non_blocking=True)
+    else:
+        _lib.require_cuda(mask, "mask")
+        _lib.require_cuda(vertex, "vertex")       # pageable host memory is rejected like CHECK_CUDA
+        if vertex.dtype != torch.float32:
+            vertex = vertex.float()
+        dev = vertex.device
     if vertex.dim() != 5 or vertex.shape[-1] != 2:
         raise RuntimeError("vertex must be [b,h,w,vn,2]")
-    if vertex.dtype != torch.float32:
-        vertex = vertex.float()
-    dev = vertex.device
     b, h, w, vn, _ = vertex.shape
     mask_mode = _lib.MASK_NONZERO if mode <= _lib.VOTE_V5 else _lib.MASK_EQ1
     mask_u8 = _mask_u8(mask, mask_mode)

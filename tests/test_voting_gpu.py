@@ -250,3 +250,59 @@ def test_full_size_properties(cuda_dev):
     torch.manual_seed(7)
     dbg2 = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn)
     assert torch.equal(dbg2["counts"], dbg["counts"]) and torch.equal(dbg2["pts"].view(torch.int32), dbg["pts"].view(torch.int32))
+
+
+@pytest.mark.parametrize("thresh", [0.999, 0.99, 0.9, 0.6])
+def test_counts_exact_on_the_cone_boundary(cuda_dev, thresh):
+    """Adversarial field for vote_count's division-free fast test: every hypothesis is (nearly) the
+    same point P, and every pixel's direction is the direction towards P rotated by the cone
+    half-angle acos(T) times (1 + eps), eps from 0 to +-1e-3 -- i.e. the cosine the reference
+    computes sits within rounding error of the threshold.  Counts must still be the reference's."""
+    from esa_pose_estimation_b200 import ransac_voting_gpu as rv
+    h, w, vn, hn = 64, 80, 3, 256
+    rng = np.random.default_rng(int(thresh * 1e4))
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    mask = np.ones((1, h, w), np.uint8)
+    vertex = np.zeros((1, 2 * vn, h, w), np.float32)
+    theta = np.arccos(np.float64(np.float32(thresh)))
+    anchors = rng.choice(h * w, 24, replace=False)                       # pixels whose rays meet in P
+    for v in range(vn):
+        px, py = [(31.37, 29.61), (-40.5, 17.25), (200.123, 90.77)][v]
+        ang = np.arctan2(py - ys, px - xs)
+        eps = rng.choice([0.0, 1e-8, -1e-8, 1e-7, -1e-7, 3e-7, -3e-7, 1e-6, -1e-6, 1e-5, -1e-5, 1e-4, -1e-4,
+                          1e-3, -1e-3], size=(h, w))
+        rot = ang + rng.choice([-1.0, 1.0], size=(h, w)) * theta * (1.0 + eps)
+        scale = rng.choice([1.0, 0.37, 2.5, 1e-3, 40.0], size=(h, w))      # |n| != 1 must not matter
+        rot.reshape(-1)[anchors] = ang.reshape(-1)[anchors]
+        vertex[0, 2 * v] = (np.cos(rot) * scale).astype(np.float32)
+        vertex[0, 2 * v + 1] = (np.sin(rot) * scale).astype(np.float32)
+    vx = vertex_hwvn2(vertex)
+    idxs = anchors[rng.integers(0, len(anchors), (1, 1, hn, vn, 2))].astype(np.int32)
+    idxs[0, 0, :8] = rng.integers(0, h * w, (8, vn, 2))                   # a few arbitrary hypotheses too
+    fn = lambda bi, r, hn_, vn_, tn: idxs[bi, r]
+    hyp, cnt = rv.ransac_voting_hypothesis(torch.from_numpy(mask).to(cuda_dev), torch.from_numpy(vx).to(cuda_dev), hn,
+                                           inlier_thresh=thresh, idxs=torch.from_numpy(idxs).to(cuda_dev))
+    hyp_o, cnt_o = ov.ransac_voting_hypothesis(mask, vx, hn, thresh, idxs_fn=fn, selection_fn=ov.default_selection_fn(0))
+    np.testing.assert_array_equal(hyp.cpu().numpy().view(np.int32), hyp_o.view(np.int32))
+    np.testing.assert_array_equal(cnt.cpu().numpy(), cnt_o)
+    assert cnt_o.max() > 100 and cnt_o.min() < cnt_o.max()               # the case is not vacuous
+
+
+def test_pinned_host_field_is_read_in_place(cuda_dev):
+    """A float32 field in pinned HOST memory (zero-copy gather over PCIe) gives bit-identical results
+    to the device-resident field; pageable host memory is rejected like the reference's CHECK_CUDA."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    b, h, w, vn, hn = 3, 72, 88, 5, 128
+    mask, vertex, _ = make_vertex_field(61, b, h, w, vn, 0.4)
+    mask[1, :, : w // 3] = 0
+    idxs, _, _, _ = _idxs_for(mask, vertex_hwvn2(vertex), hn, 1, 30000, 3)
+    i_t = torch.from_numpy(idxs).to(cuda_dev)
+    v_h = torch.from_numpy(vertex).pin_memory()
+    m_h = torch.from_numpy(mask).pin_memory()
+    dev_out = rv.voting_debug(_lib.VOTE_V4, m_h.to(cuda_dev), rv.vertex_layer_reshape(v_h.to(cuda_dev)), hn, idxs=i_t)
+    host_out = rv.voting_debug(_lib.VOTE_V4, m_h, rv.vertex_layer_reshape(v_h), hn, idxs=i_t)
+    for k in ("pts", "aux", "hyp", "counts", "tn"):
+        assert host_out[k].is_cuda
+        assert torch.equal(host_out[k].view(torch.int32), dev_out[k].view(torch.int32)), k
+    with pytest.raises(RuntimeError):
+        rv.ransac_voting_layer_v3(m_h.to(cuda_dev), rv.vertex_layer_reshape(torch.from_numpy(vertex)), hn, idxs=i_t)

@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--hn", type=int, default=512)
     ap.add_argument("--fg", type=float, default=0.25, help="foreground fraction of each crop")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--e2e-chunks", type=int, default=int(os.environ.get("EPB_E2E_CHUNKS", "0")),
+                    help="batch pieces of the host-input pipeline (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side baseline (profiling runs)")
     return ap.parse_args()
 
@@ -242,7 +244,7 @@ def run_ours(a):
         # public API on HOST buffers: the mask is copied H2D, the pinned field is read in place over
         # PCIe by the gather kernel (foreground pixels only), the poses are copied D2H
         out = pipeline.poses_from_vertex(mask_h, rv.vertex_layer_reshape(vertex_h), model_d, K_d, round_hyp_num=a.hn,
-                                         bbox_xy=bbox_d, rate=rate_d, sync_rng=False)
+                                         bbox_xy=bbox_d, rate=rate_d, sync_rng=False, chunks=a.e2e_chunks or None)
         p = pipeline.gather_poses(out["pose7"], a.batch * world) if world > 1 else out["pose7"]
         pose_h.copy_(p[rank * a.batch:(rank + 1) * a.batch] if world > 1 else p, non_blocking=True)
         return p
@@ -288,9 +290,11 @@ def run_ours(a):
     lib.epb_profile_enable(0)
     clocks = sampler.stop() if sampler else None
 
-    for _ in range(2):
+    for _ in range(max(a.warmup, 3)):
         step_e2e()
+    sampler2 = ClockSampler(local) if rank == 0 else None
     ms_e2e = timed(step_e2e, a.steps)
+    clocks_e2e = sampler2.stop() if sampler2 else None
 
     if rank != 0:
         if world > 1:
@@ -332,7 +336,7 @@ def run_ours(a):
                    "l2_policy": "inputs larger than L2 (%.0f MB of vector field per step)" % (vertex_h.numel() * 4 / 1e6),
                    "parallelism": "images sharded by batch, 1 NCCL all_gather of poses" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes,
+                "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes, "clocks": clocks_e2e,
                 "transfer": "mask cudaMemcpyAsync from pinned memory; field read zero-copy from pinned memory by "
                             "field_gather_kernel (foreground pixels only); poses D2H into pinned memory"},
         "gpu_launches": int(launches),

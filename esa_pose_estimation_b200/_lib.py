@@ -19,6 +19,7 @@ DECODE_REFINE, DECODE_ZERO_NONPOS = 1, 2
 VOTE_V3, VOTE_V4, VOTE_V5, VOTE_HYPOTHESIS, VOTE_DISTRIBUTION, VOTE_DISTRIBUTION_WITH_MEAN = range(6)
 MASK_NONZERO, MASK_EQ1 = 0, 1
 RNG_IDXS, RNG_RAW32, RNG_PHILOX = 0, 1, 2
+STAGE_ALL, STAGE_GATHER, STAGE_VOTE = 0, 1, 2
 POSE_OK, POSE_FAILED, POSE_TOO_FEW = 0, 1, 2
 
 
@@ -28,14 +29,14 @@ class VotingParams(ctypes.Structure):
                 ("min_num", c_int), ("max_num", c_int), ("topk", c_int), ("mask_mode", c_int),
                 ("sb", c_ll), ("sy", c_ll), ("sx", c_ll), ("sv", c_ll), ("sc", c_ll),
                 ("rng_mode", c_int), ("philox_seed", c_ull), ("philox_offset", c_ull),
-                ("philox_sm_count", c_int), ("philox_threads_per_sm", c_int)]
+                ("philox_sm_count", c_int), ("philox_threads_per_sm", c_int), ("stage", c_int)]
 
 
 class VotingIO(ctypes.Structure):
     _fields_ = [("mask", c_void_p), ("vertex", c_void_p), ("idxs", c_void_p), ("selection", c_void_p),
                 ("mean_in", c_void_p), ("pts", c_void_p), ("var_or_conf", c_void_p), ("hyp", c_void_p),
                 ("counts", c_void_p), ("mean", c_void_p), ("cov", c_void_p), ("tn_out", c_void_p),
-                ("status", c_void_p), ("philox_consumed", c_void_p)]
+                ("status", c_void_p), ("philox_consumed", c_void_p), ("philox_state", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/esa_pose_b200.h declares

@@ -17,6 +17,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 # --use_fast_math is never enabled: the voting kernels rely on IEEE sqrt/div.
 NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+# tuning experiments only (e.g. EPB_EXTRA_NVCC_FLAGS="-DEPB_VOTE_MINB=8")
+NVCC_FLAGS += os.environ.get("EPB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

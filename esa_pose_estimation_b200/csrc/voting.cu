@@ -124,7 +124,7 @@ __device__ __forceinline__ float torch_uniform01(unsigned r) {
 // ------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------
-constexpr int TILE_PX = 4096;  // 256 threads x 16 mask bytes
+constexpr int TILE_PX = 4096;  // 256 threads x 16 mask bytes (8 warps x 512 pixels)
 
 struct Workspace {
   int32_t* tile_counts;   // [B][T]
@@ -291,8 +291,9 @@ mask_scan_kernel(int T, int phase, int min_num, int max_num, int allow_sub, Work
 // ------------------------------------------------------------------------------------------
 __global__ void rng_offsets_kernel(int B, int rounds, unsigned long long base, unsigned long long inc_u,
                                    unsigned long long inc_r, Workspace ws,
-                                   unsigned long long* consumed, int32_t* tn_out_unused) {
+                                   unsigned long long* consumed, unsigned long long* state) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (state) base = *state;   // offset chained on the device from the previous run (batch chunks)
   unsigned long long o = base;
   for (int b = 0; b < B; ++b) {
     ws.off_u[b] = o;
@@ -301,58 +302,122 @@ __global__ void rng_offsets_kernel(int B, int rounds, unsigned long long base, u
     if (ws.live[b]) o += inc_r * (unsigned long long)rounds;
   }
   if (consumed) *consumed = o - base;
+  if (state) *state = o;
 }
 
 // ------------------------------------------------------------------------------------------
 // 4. mask_scatter: stable compaction of foreground pixel coordinates.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// Pixel ownership inside a tile of 4096: warp w owns the 512 pixels [512 w, 512 w + 512); lane l owns
+// the four quads {128 k + 4 l .. + 3}, k = 0..3.  Every warp-level access (mask bytes, field float4s)
+// is then one contiguous run -- 128 B of mask, 512 B of a field plane -- i.e. whole, aligned 128-byte
+// lines, the only access shape that keeps in-place PCIe reads of a host-resident field at full-size
+// requests (tools/micro/zerocopy_bw.cu: 51 GB/s contiguous vs 12-30 GB/s with sector-sized pieces).
+// Output order is still the row-major rank of the pixel (what torch.nonzero gives).
+template <bool PLANAR>
+__global__ void __launch_bounds__(256, 4)
 mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int mask_mode,
-                    Workspace ws, SubsampleCtx sc) {
-  const int b = blockIdx.y, tile = blockIdx.x;
-  if (!ws.live[b]) return;
+                    Workspace ws, SubsampleCtx sc, const float* __restrict__ vertex, epb_voting_params p) {
+  __shared__ int s_warp[8];
+  // grid-stride over (image, tile): a full grid for a device-resident field; for a host-resident field
+  // the launcher caps the grid at one CTA per SM -- PCIe needs ~100 KB in flight, not the machine, and
+  // a small resident footprint lets the voting kernel of the previous batch chunk keep its SMs
+  for (int work = blockIdx.x; work < T * p.B; work += gridDim.x) {
+  const int b = work / T, tile = work - b * T;
+  __syncthreads();   // s_warp of the previous trip has been consumed
+  if (!ws.live[b]) continue;
   const int HW = H * W;
   const uint8_t* m = mask + (size_t)b * HW;
-  const int p0 = tile * TILE_PX + threadIdx.x * 16;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = tile * TILE_PX + warp * 512;
   const bool sub = ws.sub[b] != 0;
   const float ratio = ws.ratio[b];
   const unsigned long long off_u = ws.off_u[b];
-  unsigned flags = 0;
-  if (p0 < HW) {
-    unsigned char bytes[16];
-    if (p0 + 16 <= HW && ((reinterpret_cast<uintptr_t>(m + p0) & 15) == 0)) {
-      *reinterpret_cast<uint4*>(bytes) = __ldg(reinterpret_cast<const uint4*>(m + p0));
+  unsigned flags[4];
+  unsigned packed = 0;   // foreground count of quad k in byte k
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int q0 = seg + k * 128 + lane * 4;
+    unsigned char bytes[4] = {0, 0, 0, 0};
+    if (q0 + 4 <= HW && ((reinterpret_cast<uintptr_t>(m + q0) & 3) == 0)) {
+      *reinterpret_cast<unsigned*>(bytes) = __ldg(reinterpret_cast<const unsigned*>(m + q0));
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) bytes[j] = (p0 + j < HW) ? m[p0 + j] : 0;
+      for (int j = 0; j < 4; ++j) bytes[j] = (q0 + j < HW) ? m[q0 + j] : 0;
     }
+    unsigned f4 = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      bool f = (p0 + j < HW) && mask_pred(bytes[j], mask_mode);
-      if (f && sub) f = keep_pixel(sc, b, HW, p0 + j, ratio, off_u);
-      flags |= (unsigned)f << j;
+    for (int j = 0; j < 4; ++j) {
+      bool f = (q0 + j < HW) && mask_pred(bytes[j], mask_mode);
+      if (f && sub) f = keep_pixel(sc, b, HW, q0 + j, ratio, off_u);
+      f4 |= (unsigned)f << j;
     }
+    flags[k] = f4;
+    packed |= (unsigned)__popc(f4) << (8 * k);
   }
-  const int mine = __popc(flags);
-  int incl = mine;
+  // byte-wise inclusive scan over the lanes (a quad-group holds at most 128 pixels: no carry between bytes)
+  unsigned incl = packed;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(FULL, incl, d);
-    if ((threadIdx.x & 31) >= d) incl += o;
+    const unsigned o = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += o;
   }
-  __shared__ int s_warp[8];
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  const unsigned tot = __shfl_sync(FULL, incl, 31);
+  const unsigned excl = incl - packed;
+  const int wtotal = (int)((tot & 255u) + ((tot >> 8) & 255u) + ((tot >> 16) & 255u) + (tot >> 24));
+  if (lane == 0) s_warp[warp] = wtotal;
   __syncthreads();
-  int wbase = 0;
-  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_warp[w];
-  int o = ws.tile_offsets[(size_t)b * T + tile] + wbase + incl - mine;
+  int wbase = ws.tile_offsets[(size_t)b * T + tile];
+  for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+  int ok[4];   // rank of the first foreground pixel of quad k
+  {
+    int kb = wbase;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ok[k] = kb + (int)((excl >> (8 * k)) & 255u);
+      kb += (int)((tot >> (8 * k)) & 255u);
+    }
+  }
   uint32_t* out = ws.fgpix + (size_t)b * HW;
-  while (flags) {
-    const int j = __ffs(flags) - 1;
-    flags &= flags - 1;
-    const int p = p0 + j;
-    const int y = p / W, x = p - y * W;
-    out[o++] = ((uint32_t)y << 16) | (uint32_t)x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int q0 = seg + k * 128 + lane * 4;
+    int o = ok[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((flags[k] >> j) & 1u) {
+        const int px = q0 + j;
+        const int y = px / W, x = px - y * W;
+        out[o++] = ((uint32_t)y << 16) | (uint32_t)x;
+      }
+  }
+  if (PLANAR && (flags[0] | flags[1] | flags[2] | flags[3])) {
+    // planar field: every (image, keypoint, component) plane is one contiguous, 64-byte-aligned H*W
+    // array (the NCHW network output); quads without foreground are not read at all
+    const float* base = vertex + b * p.sb + seg + lane * 4;
+    float2* dst = ws.direct + (size_t)b * p.vn * HW;
+    for (int v = 0; v < p.vn; ++v) {
+      const float* px = base + (long long)v * p.sv;
+      const float* py = px + p.sc;
+      float4 dx[4], dy[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (flags[k]) {
+          dx[k] = ldg_stream_f4(reinterpret_cast<const float4*>(px + k * 128));
+          dy[k] = ldg_stream_f4(reinterpret_cast<const float4*>(py + k * 128));
+        }
+      float2* d = dst + (size_t)v * HW;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float fx[4] = {dx[k].x, dx[k].y, dx[k].z, dx[k].w};
+        const float fy[4] = {dy[k].x, dy[k].y, dy[k].z, dy[k].w};
+        int o = ok[k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((flags[k] >> j) & 1u) d[o++] = make_float2(fx[j], fy[j]);
+      }
+    }
+  }
   }
 }
 
@@ -449,8 +514,10 @@ hypothesis_kernel(epb_voting_params p, Workspace ws, HypCtx hc,
 // ------------------------------------------------------------------------------------------
 // 6. vote_count: the dominant kernel (hn*vn*tn inlier tests per image).
 //
-// Persistent CTAs of 128 threads walk a list of equal-sized work units
+// One CTA of 128 threads per work unit of a device-side list of equal-sized units
 //   unit = (item of <= item_px foreground pixels of one image, keypoint, chunk of 128*R hypotheses);
+// (short CTAs instead of persistent ones so that a higher-priority stream -- the zero-copy gather of
+// the next batch chunk -- can slip in between them);
 // each thread keeps R hypotheses and their counters in registers (lanes <-> hypotheses), pixels are
 // staged through shared memory as records and broadcast to all lanes.
 //
@@ -528,7 +595,7 @@ struct VoteSmem {
 };
 
 template <int R>
-__global__ void __launch_bounds__(VOTE_THREADS)
+__global__ void __launch_bounds__(VOTE_THREADS, R <= 4 ? 8 : 4)
 vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
                   int item_px, int chunks) {
   __shared__ VoteSmem sm;
@@ -544,7 +611,9 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
   const float T = p.inlier_thresh;
   const f32x2 GG = pk2(vc.gamma, vc.gamma);
 
-  for (long long unit = blockIdx.x; unit < total; unit += gridDim.x) {
+  {
+    const long long unit = blockIdx.x;
+    if (unit >= total) return;
     const int per_item = p.vn * chunks;
     const int item = (int)(unit / per_item);
     const int rem = (int)(unit - (long long)item * per_item);
@@ -680,12 +749,13 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
       for (int it = 0; it < ntrip; ++it) {
         const int i = it * RECS;
         float m[RECS][R], w[RECS][R];
-        bool amb = false;
+        bool ambj[RECS], amb = false;
 #pragma unroll
-        for (int j = 0; j < RECS; ++j) amb |= test_record(fr[i + j], gr[i + j], m[j], w[j]);
+        for (int j = 0; j < RECS; ++j) { ambj[j] = test_record(fr[i + j], gr[i + j], m[j], w[j]); amb |= ambj[j]; }
         if (amb) {
 #pragma unroll
-          for (int j = 0; j < RECS; ++j) resolve(xr[i + j], m[j], w[j]);
+          for (int j = 0; j < RECS; ++j)
+            if (ambj[j]) resolve(xr[i + j], m[j], w[j]);
         }
 #pragma unroll
         for (int j = 0; j < RECS; ++j)
@@ -1121,6 +1191,7 @@ static bool params_ok(const epb_voting_params* p) {
   if ((long long)p->H * p->W > 0x7fffffffLL) return false;
   if (p->mode < EPB_VOTE_V3 || p->mode > EPB_VOTE_DISTRIBUTION_WITH_MEAN) return false;
   if (p->rng_mode < EPB_RNG_IDXS || p->rng_mode > EPB_RNG_PHILOX) return false;
+  if (p->stage < EPB_STAGE_ALL || p->stage > EPB_STAGE_VOTE) return false;
   if ((long long)p->hn * p->rounds > (1 << 24)) return false;
   return true;
 }
@@ -1132,16 +1203,19 @@ extern "C" size_t epb_voting_workspace_bytes(const epb_voting_params* p) {
 
 extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* io, void* workspace,
                               size_t workspace_bytes, void* stream) {
-  if (!params_ok(pp) || !io || !io->mask || !io->vertex || !workspace) return EPB_ERR_INVALID;
+  if (!params_ok(pp) || !io || !workspace) return EPB_ERR_INVALID;
   const epb_voting_params p = *pp;
+  if (p.stage != EPB_STAGE_VOTE && (!io->mask || !io->vertex)) return EPB_ERR_INVALID;
   if (p.rng_mode != EPB_RNG_PHILOX && !io->idxs) return EPB_ERR_INVALID;
   const bool is_layer = p.mode <= EPB_VOTE_V5;
   const bool is_dist = p.mode >= EPB_VOTE_DISTRIBUTION;
-  if (is_layer && !io->pts) return EPB_ERR_INVALID;
-  if ((p.mode == EPB_VOTE_V4 || p.mode == EPB_VOTE_V5) && !io->var_or_conf) return EPB_ERR_INVALID;
-  if (p.mode == EPB_VOTE_HYPOTHESIS && (!io->hyp || !io->counts)) return EPB_ERR_INVALID;
-  if (is_dist && (!io->mean || !io->cov)) return EPB_ERR_INVALID;
-  if (p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN && !io->mean_in) return EPB_ERR_INVALID;
+  if (p.stage != EPB_STAGE_GATHER) {   // the gather half produces nothing but the workspace
+    if (is_layer && !io->pts) return EPB_ERR_INVALID;
+    if ((p.mode == EPB_VOTE_V4 || p.mode == EPB_VOTE_V5) && !io->var_or_conf) return EPB_ERR_INVALID;
+    if (p.mode == EPB_VOTE_HYPOTHESIS && (!io->hyp || !io->counts)) return EPB_ERR_INVALID;
+    if (is_dist && (!io->mean || !io->cov)) return EPB_ERR_INVALID;
+    if (p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN && !io->mean_in) return EPB_ERR_INVALID;
+  }
   if (is_dist && p.topk <= 0 && p.mode == EPB_VOTE_DISTRIBUTION) return EPB_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return EPB_ERR_INVALID;
   Workspace ws = carve(p, workspace);
@@ -1162,13 +1236,14 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   // the subsample can only trigger when an image can hold more than max_num foreground pixels
   const int allow_sub = (HW > p.max_num) && (io->selection || sc.use_philox);
 
+  if (p.stage != EPB_STAGE_VOTE) {
   prof_begin(PROF_COMPACT, s);
   mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 0, ws, sc);
   EPB_RETURN_IF(check_launch());
   mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 0, p.min_num, p.max_num, allow_sub, ws);
   EPB_RETURN_IF(check_launch());
   rng_offsets_kernel<<<1, 32, 0, s>>>(p.B, p.rounds, p.philox_offset, lu.inc, lr.inc, ws,
-                                      io->philox_consumed, nullptr);
+                                      io->philox_consumed, io->philox_state);
   EPB_RETURN_IF(check_launch());
   if (allow_sub) {
     mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 1, ws, sc);
@@ -1176,11 +1251,31 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 1, p.min_num, p.max_num, allow_sub, ws);
     EPB_RETURN_IF(check_launch());
   }
-  mask_scatter_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc);
-  EPB_RETURN_IF(check_launch());
-  field_gather_kernel<<<dim3((HW + 255) / 256, p.B), 256, 0, s>>>(io->vertex, p, ws);
-  EPB_RETURN_IF(check_launch());
+  // planar field (NCHW network output seen through vertex_layer_reshape): gather fused into the scatter
+  const bool planar = p.sx == 1 && p.sy == p.W && (HW % 16) == 0 && (p.sb % 16) == 0 && (p.sv % 16) == 0 &&
+                      (p.sc % 16) == 0 && (reinterpret_cast<uintptr_t>(io->vertex) & 63) == 0;
+  if (planar) {
+    cudaPointerAttributes attr;
+    const bool host_field = cudaPointerGetAttributes(&attr, io->vertex) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    int dev_id = 0, sm_n = 148;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sm_n, cudaDevAttrMultiProcessorCount, dev_id);
+    const long long work = (long long)T * p.B;
+    static const int per_sm = [] { const char* e = getenv("EPB_GATHER_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
+    const long long cap = (long long)sm_n * (per_sm > 0 ? per_sm : 1);
+    const unsigned g = (unsigned)(host_field && work > cap ? cap : work);
+    mask_scatter_kernel<true><<<g, 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p);
+    EPB_RETURN_IF(check_launch());
+  } else {
+    mask_scatter_kernel<false><<<(unsigned)((long long)T * p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p);
+    EPB_RETURN_IF(check_launch());
+    field_gather_kernel<<<dim3((HW + 255) / 256, p.B), 256, 0, s>>>(io->vertex, p, ws);
+    EPB_RETURN_IF(check_launch());
+  }
   prof_end(PROF_COMPACT, s);
+  }
+  if (p.stage == EPB_STAGE_GATHER) return EPB_OK;
   if (io->tn_out)
     EPB_RETURN_IF(check_api(cudaMemcpyAsync(io->tn_out, ws.tn, (size_t)p.B * 4, cudaMemcpyDeviceToDevice, s)));
 
@@ -1197,7 +1292,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     EPB_RETURN_IF(check_launch());
   }
   {
-    // persistent CTAs over equal-sized work units (pixel item x keypoint x hypothesis chunk)
+    // equal-sized work units (pixel item x keypoint x hypothesis chunk), listed on the device
     int R = HN <= 256 ? 2 : (HN <= 512 ? 4 : g_vote_r_large);
     {  // tuning hook (profiling only): EPB_VOTE_R=2|4|8 overrides the hypotheses per thread
       static const int forced = [] { const char* e = getenv("EPB_VOTE_R"); return e ? atoi(e) : 0; }();
@@ -1216,16 +1311,33 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     int item_px = 4 * VOTE_TILE;
     while (item_px > VOTE_TILE &&
            (long long)p.B * p.vn * chunks * ((HW + item_px - 1) / item_px) < 4 * slots) item_px >>= 1;
+    {  // tuning hook (profiling only)
+      static const int forced = [] { const char* e = getenv("EPB_VOTE_ITEM"); return e ? atoi(e) : 0; }();
+      if (forced >= VOTE_TILE) item_px = forced;
+    }
     const long long max_units = (long long)p.B * p.vn * chunks * ((HW + item_px - 1) / item_px);
-    const unsigned grid = (unsigned)(max_units < slots ? max_units : slots);
+    if (max_units > 0x7fffffffLL) return EPB_ERR_INVALID;
+    const unsigned grid = (unsigned)max_units;   // units beyond the device-side total exit at once
     const VoteConsts vc = vote_consts(p.inlier_thresh, p.H, p.W);
     vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
     EPB_RETURN_IF(check_launch());
     EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
+    // Split runs overlap this kernel with the gather stage of the next batch chunk on a high-priority
+    // stream.  Its small kernels can only start when an SM has registers to spare, so the vote CTAs are
+    // held two below full occupancy there (unused dynamic shared memory is the occupancy knob; measured:
+    // gather 0.75 -> 0.58 ms per chunk under a concurrent vote, vote 0.68 -> 0.61 ms).
+    size_t pad = 0;
+    if (p.stage == EPB_STAGE_VOTE && occ >= 4) {
+      static const int knob = [] { const char* e = getenv("EPB_VOTE_HEADROOM"); return e ? atoi(e) : 2; }();
+      const int want = occ - knob;
+      const size_t per_sm = 227 * 1024, used = sizeof(VoteSmem) + 1024;
+      if (knob > 0 && want >= 1 && per_sm / (size_t)want > used) pad = per_sm / (size_t)(want + 1) + 1024 > used
+                                                                          ? per_sm / (size_t)(want + 1) + 1024 - used : 0;
+    }
     ProfScope ps(PROF_VOTE_COUNT, s);
-    if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
-    else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
-    else vote_count_kernel<8><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+    if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
+    else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
+    else vote_count_kernel<8><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
     EPB_RETURN_IF(check_launch());
   }
   if (io->counts) {

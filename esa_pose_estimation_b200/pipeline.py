@@ -39,13 +39,119 @@ def poses_from_keypoints(kpts, p3d_model, K, bbox_xy=None, rate=None, weights=No
 
 
 def poses_from_vertex(mask, vertex, p3d_model, K, round_hyp_num=512, inlier_thresh=0.999, min_num=5,
-                      max_num=30000, bbox_xy=None, rate=None, **kw):
+                      max_num=30000, bbox_xy=None, rate=None, chunks=None, **kw):
     """mask [B,H,W], vertex [B,H,W,vn,2] (e.g. vertex_layer_reshape of the NCHW network output).
-    -> dict(pose7, rt6, epnp_rt34, status, kpts)."""
-    kpts = _voting.ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=inlier_thresh,
-                                          min_num=min_num, max_num=max_num, **kw)
+    -> dict(pose7, rt6, epnp_rt34, status, kpts).
+
+    `vertex` (and `mask`) may live in PINNED host memory.  The batch is then cut into `chunks`
+    pieces (default 4 when B >= 16): a high-priority side stream compacts the foreground and reads
+    the field of piece i+1 in place over PCIe while the current stream votes and solves piece i."""
+    host = isinstance(vertex, torch.Tensor) and not vertex.is_cuda
+    b = vertex.shape[0]
+    if chunks is None:
+        chunks = 4 if (host and b >= 16) else 1
+    chunks = max(1, min(int(chunks), b))
+    if not host or chunks == 1:
+        kpts = _voting.ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=inlier_thresh,
+                                              min_num=min_num, max_num=max_num, **kw)
+        out = poses_from_keypoints(kpts, p3d_model, K, bbox_xy=bbox_xy, rate=rate)
+        out["kpts"] = kpts
+        return out
+    return _poses_from_host_vertex(mask, vertex, p3d_model, K, round_hyp_num, inlier_thresh, min_num, max_num,
+                                   bbox_xy, rate, chunks, kw)
+
+
+class _HostPipe:
+    """Per (device, stream) state of the host-input pipeline: the high-priority gather stream and a
+    ring of two workspace sets, so that the gather of call n+1 may start while call n still votes."""
+
+    def __init__(self, dev):
+        self.gs = torch.cuda.Stream(device=dev, priority=-1)
+        self.sets = [None, None]          # each: dict(ws=[tensors], done=[events], need=int)
+        self.turn = 0
+
+
+_host_pipes = {}
+
+
+def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max_num, bbox_xy, rate, chunks, kw):
+    from . import _lib
+    dev = p3d_model.device if p3d_model.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    b, h, w, vn, _ = vertex.shape
+    cur = torch.cuda.current_stream(dev)
+    key = (dev.index, cur.cuda_stream)
+    pipe = _host_pipes.get(key)
+    if pipe is None:
+        pipe = _host_pipes[key] = _HostPipe(dev)
+    gs = pipe.gs
+    bounds = [shard_range(b, i, chunks) for i in range(chunks)]
+    per = max(e - s for s, e in bounds)
+    need = _voting.workspace_bytes(per, h, w, vn, hn)
+    st = pipe.sets[pipe.turn]
+    if st is None or len(st["ws"]) < chunks or st["need"] < need:
+        st = pipe.sets[pipe.turn] = dict(
+            ws=[torch.empty((need,), dtype=torch.uint8, device=dev) for _ in range(chunks)],
+            done=[None] * chunks, need=need)
+    pipe.turn ^= 1
+    wss = st["ws"]
+    kw = dict(kw)
+    sync_rng = kw.pop("sync_rng", True)
+    per_image = {k: kw.pop(k) for k in ("idxs", "selection") if kw.get(k) is not None}
+    philox = "idxs" not in per_image
+    gen = rng_state = None
+    if philox:                                # one torch generator stream across the chunks
+        gen = torch.cuda.default_generators[dev.index]
+        start = gen.get_offset()
+        with torch.cuda.stream(gs):           # lives on the gather stream: no ordering against `cur` needed
+            rng_state = torch.full((1,), start, dtype=torch.int64, device=dev)
+        kw["rng_state"] = rng_state
+
+    def chunk_kw(s, e):
+        d = dict(kw)
+        for k, t in per_image.items():
+            d[k] = t[s:e]
+        return d
+
+    # device-resident arguments were produced on the current stream; host buffers need no ordering
+    if mask.is_cuda or per_image:
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        gs.wait_event(ready)
+    events, masks_d = [], []
+    with torch.cuda.stream(gs):
+        for i, (s, e) in enumerate(bounds):
+            if st["done"][i] is not None:
+                gs.wait_event(st["done"][i])          # the call two turns ago has consumed this workspace
+            m = mask[s:e]
+            m_d = m if m.is_cuda else m.to(dev, non_blocking=True)
+            _voting._run(_lib.VOTE_V3, m_d, vertex[s:e], hn, 1, thresh, min_num, max_num,
+                         stage=_lib.STAGE_GATHER, workspace=wss[i], **chunk_kw(s, e))
+            ev = torch.cuda.Event()
+            ev.record(gs)
+            events.append(ev)
+            masks_d.append(m_d)
+    kps = []
+    for i, (s, e) in enumerate(bounds):
+        cur.wait_event(events[i])
+        kps.append(_voting._run(_lib.VOTE_V3, masks_d[i], vertex[s:e], hn, 1, thresh, min_num, max_num,
+                                stage=_lib.STAGE_VOTE, workspace=wss[i], **chunk_kw(s, e))["pts"])
+        done = torch.cuda.Event()
+        done.record(cur)
+        st["done"][i] = done
+    for m_d in masks_d:
+        m_d.record_stream(cur)
+    # the pose solve is latency-bound (one warp per image): one launch over the whole batch
+    kpts = torch.cat(kps, 0)
     out = poses_from_keypoints(kpts, p3d_model, K, bbox_xy=bbox_xy, rate=rate)
     out["kpts"] = kpts
+    if philox:
+        if sync_rng:                          # exact: what the reference's loop would have consumed
+            cur.wait_stream(gs)
+            gen.set_offset(int(rng_state.item()))
+        else:                                 # data-independent upper bound, no synchronisation
+            props = torch.cuda.get_device_properties(dev)
+            inc = _voting._rng_layout(hn * vn * 2, props) + (_voting._rng_layout(h * w, props) if h * w > max_num else 0)
+            gen.set_offset(start + b * inc)
     return out
 
 

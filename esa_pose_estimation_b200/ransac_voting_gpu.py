@@ -64,7 +64,14 @@ def _rng_layout(numel, props):
 
 
 def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_in=None, idxs=None,
-         raw32=False, selection=None, sync_rng=True, want_hyp=False, want_status=False):
+         raw32=False, selection=None, sync_rng=True, want_hyp=False, want_status=False,
+         stage=_lib.STAGE_ALL, workspace=None, rng_state=None):
+    """One epb_voting_run.  `stage` / `workspace` split a run in two stream-ordered halves
+    (STAGE_GATHER fills `workspace`, STAGE_VOTE consumes it; same arguments both times) so that
+    pipeline.py can overlap the PCIe read of one batch chunk with the voting of the previous one.
+    The torch generator is read and advanced by the gather half only; with `rng_state` (a device
+    int64 [1] tensor holding the generator offset) consecutive runs chain their Philox offsets on the
+    device and the caller advances the torch generator once at the end."""
     if isinstance(vertex, torch.Tensor) and not vertex.is_cuda and vertex.is_pinned():
         # Host-resident network output: the field is read in place over PCIe by field_gather_kernel
         # (zero-copy, foreground pixels only); only the mask is copied to the device.
@@ -118,6 +125,11 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
         gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
         p.philox_seed = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF
         p.philox_offset = gen.get_offset()
+        if stage == _lib.STAGE_VOTE or rng_state is not None:
+            gen = None                                    # advanced by the gather half / by the caller
+        if rng_state is not None:
+            io.philox_state = _lib.ptr(rng_state)
+            keep.append(rng_state)
         if selection is not None:
             selection = selection.to(device=dev, dtype=torch.float32).contiguous()
             io.selection = _lib.ptr(selection)
@@ -125,17 +137,22 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
 
     out = {}
     f32 = dict(dtype=torch.float32, device=dev)
-    if mode <= _lib.VOTE_V5:
+    p.stage = stage
+    if stage == _lib.STAGE_GATHER:
+        mode_outputs = False
+    else:
+        mode_outputs = True
+    if mode_outputs and mode <= _lib.VOTE_V5:
         out["pts"] = torch.empty((b, vn, 2), **f32)
         io.pts = _lib.ptr(out["pts"])
         if mode != _lib.VOTE_V3:
             out["aux"] = torch.empty((b, vn), **f32)
             io.var_or_conf = _lib.ptr(out["aux"])
-    if mode == _lib.VOTE_HYPOTHESIS or want_hyp:
+    if mode_outputs and (mode == _lib.VOTE_HYPOTHESIS or want_hyp):
         out["hyp"] = torch.empty((b, hn_total, vn, 2), **f32)
         out["counts"] = torch.empty((b, hn_total, vn), dtype=torch.int32, device=dev)
         io.hyp, io.counts = _lib.ptr(out["hyp"]), _lib.ptr(out["counts"])
-    if mode >= _lib.VOTE_DISTRIBUTION:
+    if mode_outputs and mode >= _lib.VOTE_DISTRIBUTION:
         out["mean"] = torch.empty((b, vn, 2), **f32)
         out["cov"] = torch.empty((b, vn, 2, 2), **f32)
         io.mean, io.cov = _lib.ptr(out["mean"]), _lib.ptr(out["cov"])
@@ -143,9 +160,10 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
             mean_in = mean_in.to(device=dev, dtype=torch.float32).contiguous()
             io.mean_in = _lib.ptr(mean_in)
             keep.append(mean_in)
-    out["tn"] = torch.empty((b,), dtype=torch.int32, device=dev)
-    io.tn_out = _lib.ptr(out["tn"])
-    if want_status:
+    if mode_outputs:
+        out["tn"] = torch.empty((b,), dtype=torch.int32, device=dev)
+        io.tn_out = _lib.ptr(out["tn"])
+    if want_status and mode_outputs:
         out["status"] = torch.zeros((b, vn), dtype=torch.int32, device=dev)
         io.status = _lib.ptr(out["status"])
     consumed = None
@@ -158,7 +176,14 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
     nbytes = lib.epb_voting_workspace_bytes(p)
     if nbytes == 0:
         raise RuntimeError("epb_voting_workspace_bytes: invalid parameters")
-    ws = _workspace(dev, nbytes + 256)
+    if workspace is None:
+        if stage != _lib.STAGE_ALL:
+            raise RuntimeError("a split run needs an explicit workspace shared by both halves")
+        ws = _workspace(dev, nbytes + 256)
+    else:
+        ws = workspace
+        if ws.numel() < nbytes + 256 or not ws.is_cuda:
+            raise RuntimeError("workspace too small: need %d bytes" % (nbytes + 256))
     base = (ws.data_ptr() + 255) & ~255
     with torch.cuda.device(dev):
         st = lib.epb_voting_run(p, io, _lib.c_void_p(base), nbytes, _lib.stream_ptr())
@@ -170,6 +195,17 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
             inc = rounds * _rng_layout(hn * vn * 2, props) + (_rng_layout(h * w, props) if h * w > max_num else 0)
             gen.set_offset(p.philox_offset + b * inc)
     return out
+
+
+def workspace_bytes(b, h, w, vn, hn, rounds=1):
+    """Bytes of caller-owned workspace one run over [b,h,w,vn,2] needs (+ alignment slack)."""
+    p = _lib.VotingParams()
+    p.mode, p.B, p.H, p.W, p.vn, p.hn, p.rounds = _lib.VOTE_V3, b, h, w, vn, int(hn), int(rounds)
+    p.rng_mode = _lib.RNG_PHILOX
+    n = _lib.load().epb_voting_workspace_bytes(p)
+    if n == 0:
+        raise RuntimeError("epb_voting_workspace_bytes: invalid parameters")
+    return int(n) + 256
 
 
 def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,

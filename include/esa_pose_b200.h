@@ -113,6 +113,16 @@ enum {
   EPB_RNG_PHILOX = 2  /* Philox4x32-10 in the layout of torch's CUDA random_() / uniform_() */
 };
 
+enum {
+  EPB_STAGE_ALL = 0,    /* the whole run */
+  EPB_STAGE_GATHER = 1, /* only: foreground compaction + gather of the field into the workspace.  This
+                           is the only stage that reads `mask` and `vertex`; run it on a separate
+                           (high-priority) stream to overlap the PCIe read of a host-resident field
+                           of batch chunk i+1 with the voting of chunk i */
+  EPB_STAGE_VOTE = 2    /* only: hypotheses, inlier counts, winners / distribution, on a workspace
+                           that EPB_STAGE_GATHER filled with the same parameters */
+};
+
 typedef struct {
   int mode;             /* EPB_VOTE_* */
   int B, H, W, vn;
@@ -132,13 +142,18 @@ typedef struct {
   unsigned long long philox_offset; /* torch generator offset before the call */
   int philox_sm_count;  /* multiProcessorCount torch would see (grid clamp of its RNG kernels) */
   int philox_threads_per_sm; /* maxThreadsPerMultiProcessor */
+  int stage;            /* EPB_STAGE_* */
 } epb_voting_params;
 
 size_t epb_voting_workspace_bytes(const epb_voting_params* p);
 
 typedef struct {
   const uint8_t* mask;      /* [B,H,W] u8 */
-  const float* vertex;      /* strided, see params */
+  const float* vertex;      /* strided, see params.  Read exactly once, foreground pixels only, by
+                               one gather kernel: it may be DEVICE memory or page-locked HOST memory
+                               mapped into the device address space (cudaHostAlloc / cudaHostRegister
+                               under UVA), in which case only the foreground part of the field crosses
+                               PCIe (zero-copy) and no staging copy of the field is needed */
   const int32_t* idxs;      /* EPB_RNG_IDXS / RAW32: [B,rounds,hn,vn,2]; else NULL */
   const float* selection;   /* optional [B,H,W] f32 uniform draws for the max_num subsample
                                (EPB_RNG_IDXS / RAW32); NULL -> Philox or no subsample possible */
@@ -152,6 +167,10 @@ typedef struct {
   int32_t* tn_out;          /* optional [B]: foreground count after the subsample */
   int32_t* status;          /* optional [B,vn]: 0 ok, 1 image skipped (< min_num), 2 singular refine */
   unsigned long long* philox_consumed; /* optional [1]: generator offset increment (EPB_RNG_PHILOX) */
+  unsigned long long* philox_state;    /* optional [1], in/out: when given, the generator offset is read
+                                          from here instead of params.philox_offset and the offset after
+                                          the run is written back, so consecutive runs (batch chunks)
+                                          continue one torch generator stream without a host round trip */
 } epb_voting_io;
 
 int epb_voting_run(const epb_voting_params* p, const epb_voting_io* io, void* workspace,

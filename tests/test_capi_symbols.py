@@ -33,9 +33,22 @@ def test_library_builds_loads_and_exports_all_symbols():
 
 def test_struct_layout_matches_header():
     from esa_pose_estimation_b200 import _lib
-    # epb_voting_params: 7 int + float + 4 int + 5 long long + int + 2 ull + 2 int
-    assert ctypes.sizeof(_lib.VotingParams) == 120
-    assert ctypes.sizeof(_lib.VotingIO) == 14 * ctypes.sizeof(ctypes.c_void_p)
+    # the C compiler's own layout of the header's structs (a plain C translation unit: the header is C)
+    import subprocess, tempfile
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "esa_pose_b200.h"\n'
+           'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(epb_voting_params), sizeof(epb_voting_io),'
+           ' offsetof(epb_voting_params, sb), offsetof(epb_voting_params, philox_seed),'
+           ' offsetof(epb_voting_params, stage)); return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o",
+                        os.path.join(d, "t")], check=True)
+        sz_p, sz_io, off_sb, off_seed, off_stage = map(int, subprocess.run([os.path.join(d, "t")], capture_output=True,
+                                                                           text=True, check=True).stdout.split())
+    assert ctypes.sizeof(_lib.VotingParams) == sz_p
+    assert ctypes.sizeof(_lib.VotingIO) == sz_io == 15 * ctypes.sizeof(ctypes.c_void_p)
+    assert _lib.VotingParams.sb.offset == off_sb and _lib.VotingParams.philox_seed.offset == off_seed
+    assert _lib.VotingParams.stage.offset == off_stage
     lib = _lib.load()
     p = _lib.VotingParams()
     assert lib.epb_voting_workspace_bytes(p) == 0                      # invalid (all-zero) parameters

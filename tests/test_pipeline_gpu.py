@@ -69,3 +69,25 @@ def test_vertex_to_pose_matches_oracle(cuda_dev):
 def test_smoke_entry(cuda_dev):
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_host_field_chunked_pipeline_equals_device_run(cuda_dev):
+    """Pinned host field, batch cut in chunks on two streams (gather of chunk i+1 under the voting
+    of chunk i): keypoints, poses and the torch generator end state are identical to one device run."""
+    from esa_pose_estimation_b200 import pipeline, ransac_voting_gpu as rv
+    B, vn, S, hn = 20, 5, 64, 128
+    mask, vertex, _ = make_vertex_field(71, B, S, S, vn, 0.4, noise_deg=1.5)
+    mask[3] = 0                                                          # a skipped image inside a chunk
+    model = torch.from_numpy(tango_model(vn, seed=9)).to(cuda_dev)
+    K = torch.from_numpy(np.array([[120.0, 0, 32], [0, 120.0, 32], [0, 0, 1]])).to(cuda_dev)
+    m_h, v_h = torch.from_numpy(mask).pin_memory(), torch.from_numpy(vertex).pin_memory()
+    torch.manual_seed(5)
+    ref = pipeline.poses_from_vertex(m_h.to(cuda_dev), rv.vertex_layer_reshape(v_h.to(cuda_dev)), model, K, round_hyp_num=hn)
+    off_ref = torch.cuda.default_generators[cuda_dev.index or 0].get_offset()
+    for chunks in (4, 3, 1):
+        torch.manual_seed(5)
+        out = pipeline.poses_from_vertex(m_h, rv.vertex_layer_reshape(v_h), model, K, round_hyp_num=hn, chunks=chunks)
+        assert torch.cuda.default_generators[cuda_dev.index or 0].get_offset() == off_ref
+        assert torch.equal(out["kpts"].view(torch.int32), ref["kpts"].view(torch.int32)), chunks
+        live = torch.ones(B, dtype=torch.bool); live[3] = False
+        assert torch.equal(out["pose7"][live].view(torch.int32), ref["pose7"][live].view(torch.int32)), chunks

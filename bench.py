@@ -133,7 +133,7 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = a.cpu_sample or max(cores, 8)
+    per_step = a.cpu_sample or max(4 * cores, 16)
     for _ in range(min(a.warmup, 1)):
         cpu_run(a, cores, cores)
     t_all, n_all = 0.0, 0
@@ -163,7 +163,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -172,7 +172,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -345,16 +345,22 @@ def run_ours(a):
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_s * 1e3,
                      "share_of_step": (vote_ms / a.steps) / step_ms if step_ms > 0 else None,
                      "note": "FP32-ALU-bound at this foreground (SURVEY 8d): see alu",
+                     # the kernel's real bound: FP32 issue.  Algorithmic cost of one (hypothesis, pixel) test in the
+                     # affine formulation: 2 + 2 FMAs for the two forms, 1 subtraction, 1 band FMA
                      "alu": {"pair_tests_per_launch": evals, "pair_tests_per_s": evals / per_launch_s if per_launch_s else 0,
+                             "algorithmic_fp32_lane_ops_per_test": 6,
+                             "achieved_lane_ops_per_s": 6 * evals / per_launch_s if per_launch_s else 0,
                              "fp32_lane_ops_peak_per_s": lane_ops_peak,
-                             "lane_ops_per_test_at_peak": lane_ops_peak * per_launch_s / evals if evals else None}},
+                             "frac": (6 * evals / per_launch_s) / lane_ops_peak if per_launch_s and lane_ops_peak else None,
+                             "lane_op_slots_per_test": lane_ops_peak * per_launch_s / evals if evals else None}},
         "kernel_ms_per_step": {k: v[0] / a.steps for k, v in prof.items()},
         "clocks": clocks,
     }
     # --- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_img = a.cpu_sample or max(2 * cores, 8)
+        # bounded sample sized for ~10-20 s of host work (about 0.7 s per image and core)
+        n_img = a.cpu_sample or max(20 * cores, 32)
         try:
             v, dt = cpu_run(a, n_img, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

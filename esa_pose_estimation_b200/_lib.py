@@ -16,8 +16,8 @@ STATUS_NAMES = {0: "EPB_OK", 1: "EPB_ERR_INVALID", 2: "EPB_ERR_CUDA", 3: "EPB_ER
                 4: "EPB_ERR_NO_DEVICE"}
 
 DECODE_REFINE, DECODE_ZERO_NONPOS = 1, 2
-VOTE_V3, VOTE_V4, VOTE_V5, VOTE_HYPOTHESIS, VOTE_DISTRIBUTION, VOTE_DISTRIBUTION_WITH_MEAN = range(6)
-MASK_NONZERO, MASK_EQ1 = 0, 1
+VOTE_V3, VOTE_V4, VOTE_V5, VOTE_HYPOTHESIS, VOTE_DISTRIBUTION, VOTE_DISTRIBUTION_WITH_MEAN, VOTE_V1, VOTE_V2 = range(8)
+MASK_NONZERO, MASK_EQ1, MASK_CLASS = 0, 1, 2
 RNG_IDXS, RNG_RAW32, RNG_PHILOX = 0, 1, 2
 STAGE_ALL, STAGE_GATHER, STAGE_VOTE = 0, 1, 2
 POSE_OK, POSE_FAILED, POSE_TOO_FEW = 0, 1, 2
@@ -29,7 +29,8 @@ class VotingParams(ctypes.Structure):
                 ("min_num", c_int), ("max_num", c_int), ("topk", c_int), ("mask_mode", c_int),
                 ("sb", c_ll), ("sy", c_ll), ("sx", c_ll), ("sv", c_ll), ("sc", c_ll),
                 ("rng_mode", c_int), ("philox_seed", c_ull), ("philox_offset", c_ull),
-                ("philox_sm_count", c_int), ("philox_threads_per_sm", c_int), ("stage", c_int)]
+                ("philox_sm_count", c_int), ("philox_threads_per_sm", c_int), ("stage", c_int),
+                ("classes", c_int), ("refine_iters", c_int)]
 
 
 class VotingIO(ctypes.Structure):
@@ -64,6 +65,7 @@ SIGNATURES = {
     "epb_rt34_to_rt6": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "epb_pose_pipeline": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "epb_cov_to_weights": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "epb_esa_score": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -892,6 +892,27 @@ __global__ void rt34_to_rt6_kernel(const double* __restrict__ rt34, int B, doubl
   o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = m[3]; o[4] = m[7]; o[5] = m[11];
 }
 
+// lib/utils/evaluation_utils.py:170-181: per keypoint W = inv(sqrtm(cov)) -> (wxx, wxy, wyy); zero
+// weights when cov[0][0] < 1e-6 or any entry is NaN (the reference's guard) -- and, by definition here,
+// when cov is not positive definite (scipy's sqrtm turns complex there and the reference breaks).
+// 2x2 SPD closed form: sqrtm(A) = (A + s I) / t with s = sqrt(det A), t = sqrt(tr A + 2 s).
+__global__ void cov_to_weights_kernel(const float* __restrict__ cov, int n, double* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* c = cov + 4 * (size_t)i;
+  const double a = c[0], b01 = c[1], b10 = c[2], d = c[3];
+  double* o = w + 3 * (size_t)i;
+  o[0] = o[1] = o[2] = 0.0;
+  if (c[0] < 1e-6f || isnan(c[0]) || isnan(c[1]) || isnan(c[2]) || isnan(c[3])) return;
+  const double b = 0.5 * (b01 + b10);
+  const double det = a * d - b * b;
+  if (!(det > 0.0) || !(d > 0.0)) return;
+  const double s = sqrt(det), t = sqrt(a + d + 2.0 * s);
+  // S = (A + s I) / t;  det S = s;  inv(S) = [[S11, -S01], [-S01, S00]] / s
+  const double s00 = (a + s) / t, s01 = b / t, s11 = (d + s) / t;
+  o[0] = s11 / s; o[1] = -s01 / s; o[2] = s00 / s;
+}
+
 // val.py:172-228 for a batch: one warp per frame, lane k <-> keypoint k (K <= 32)
 __global__ void __launch_bounds__(POSE_WARPS * 32)
 pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ maxvals,
@@ -1035,6 +1056,13 @@ extern "C" int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* str
   if (!rt34 || !rt6 || B < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   rt34_to_rt6_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rt34, B, rt6);
+  return check_launch();
+}
+
+extern "C" int epb_cov_to_weights(const float* cov, int n, double* w2d, void* stream) {
+  if (!cov || !w2d || n < 0) return EPB_ERR_INVALID;
+  if (n == 0) return EPB_OK;
+  cov_to_weights_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cov, n, w2d);
   return check_launch();
 }
 

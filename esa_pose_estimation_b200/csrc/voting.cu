@@ -173,8 +173,11 @@ __host__ inline Workspace carve(const epb_voting_params& p, void* base) {
   return w;
 }
 
-__device__ __forceinline__ bool mask_pred(unsigned m, int mask_mode) {
-  return mask_mode == EPB_MASK_EQ1 ? (m == 1u) : (m != 0u);
+// Multi-class drivers (v1 / v2) run every (image, class) pair as one "virtual image": virtual index
+// bv = image * classes + (class - 1); mask and field are addressed with bv / classes, everything in the
+// workspace and the outputs with bv.
+__device__ __forceinline__ bool mask_pred(unsigned m, int mask_mode, unsigned cls) {
+  return mask_mode == EPB_MASK_CLASS ? (m == cls) : mask_mode == EPB_MASK_EQ1 ? (m == 1u) : (m != 0u);
 }
 
 // foreground predicate of pixel `p` of image `b` including the optional max_num subsample
@@ -199,11 +202,12 @@ __device__ __forceinline__ bool keep_pixel(const SubsampleCtx& sc, int b, size_t
 //    only for images flagged in ws.sub.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-mask_count_kernel(const uint8_t* __restrict__ mask, int HW, int T, int mask_mode, int phase,
+mask_count_kernel(const uint8_t* __restrict__ mask, int HW, int T, int mask_mode, int classes, int phase,
                   Workspace ws, SubsampleCtx sc) {
   const int b = blockIdx.y, tile = blockIdx.x;
   if (phase == 1 && !ws.sub[b]) return;
-  const uint8_t* m = mask + (size_t)b * HW;
+  const uint8_t* m = mask + (size_t)(b / classes) * HW;
+  const unsigned cls = (unsigned)(b % classes) + 1u;
   const int p0 = tile * TILE_PX + threadIdx.x * 16;
   int cnt = 0;
   float ratio = 0.f;
@@ -219,7 +223,7 @@ mask_count_kernel(const uint8_t* __restrict__ mask, int HW, int T, int mask_mode
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      bool f = (p0 + j < HW) && mask_pred(bytes[j], mask_mode);
+      bool f = (p0 + j < HW) && mask_pred(bytes[j], mask_mode, cls);
       if (f && phase == 1) f = keep_pixel(sc, b, HW, p0 + j, ratio, off_u);
       cnt += f;
     }
@@ -327,7 +331,8 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
   __syncthreads();   // s_warp of the previous trip has been consumed
   if (!ws.live[b]) continue;
   const int HW = H * W;
-  const uint8_t* m = mask + (size_t)b * HW;
+  const uint8_t* m = mask + (size_t)(b / p.classes) * HW;
+  const unsigned cls = (unsigned)(b % p.classes) + 1u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int seg = tile * TILE_PX + warp * 512;
   const bool sub = ws.sub[b] != 0;
@@ -348,7 +353,7 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
     unsigned f4 = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      bool f = (q0 + j < HW) && mask_pred(bytes[j], mask_mode);
+      bool f = (q0 + j < HW) && mask_pred(bytes[j], mask_mode, cls);
       if (f && sub) f = keep_pixel(sc, b, HW, q0 + j, ratio, off_u);
       f4 |= (unsigned)f << j;
     }
@@ -394,7 +399,7 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
   if (PLANAR && (flags[0] | flags[1] | flags[2] | flags[3])) {
     // planar field: every (image, keypoint, component) plane is one contiguous, 64-byte-aligned H*W
     // array (the NCHW network output); quads without foreground are not read at all
-    const float* base = vertex + b * p.sb + seg + lane * 4;
+    const float* base = vertex + (b / p.classes) * p.sb + seg + lane * 4;
     float2* dst = ws.direct + (size_t)b * p.vn * HW;
     for (int v = 0; v < p.vn; ++v) {
       const float* px = base + (long long)v * p.sv;
@@ -436,7 +441,7 @@ field_gather_kernel(const float* __restrict__ vertex, epb_voting_params p, Works
   if (!ws.live[b] || t >= ws.tn[b]) return;
   const size_t HW = (size_t)p.H * p.W;
   const uint32_t q = ws.fgpix[(size_t)b * HW + t];
-  const float* src = vertex + b * p.sb + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
+  const float* src = vertex + (b / p.classes) * p.sb + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
   float2* dst = ws.direct + (size_t)b * p.vn * HW + t;
   int v = 0;
   for (; v + 4 <= p.vn; v += 4) {  // 8 independent loads in flight per thread (PCIe / HBM latency)
@@ -897,30 +902,53 @@ winner_refine_kernel(epb_voting_params p, Workspace ws,
                           : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  const float2 win = s_pt;
+  float2 win = s_pt;
   const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
   const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
-  // pass 1: inliers of the winner and the normal equations
-  double acc[7] = {0, 0, 0, 0, 0, 0, 0};  // a00 a01 a11 b0 b1 sum(bb^2) count
-  for (int t = threadIdx.x; t < tn; t += 256) {
-    const uint32_t q = __ldg(fp + t);
-    const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
-    const float2 d = __ldg(dir + t);
-    const float dx = d.x, dy = d.y;
-    if (vote_exact(cx, cy, dx, dy, dir_norm(dx, dy), win.x, win.y, p.inlier_thresh)) {
-      const double nx = dy, ny = -(double)dx;  // normal = (d_y, -d_x), :580-581
-      const double bb = nx * cx + ny * cy;
-      acc[0] += nx * nx; acc[1] += nx * ny; acc[2] += ny * ny;
-      acc[3] += nx * bb; acc[4] += ny * bb; acc[5] += bb * bb; acc[6] += 1.0;
-    }
+  if (p.mode == EPB_VOTE_V1) {   // ransac_voting_layer (:10-97): the winning hypothesis itself
+    if (threadIdx.x == 0) { *out = win; if (st) *st = 0; }
+    return;
   }
-  block_sum_d<7>(acc, s_red);
-  const double det = acc[0] * acc[2] - acc[1] * acc[1];
-  const bool singular = !(fabs(det) > 0.0) || !isfinite(det);
-  double px = NAN, py = NAN;
-  if (!singular) {
-    px = (acc[2] * acc[3] - acc[1] * acc[4]) / det;
-    py = (acc[0] * acc[4] - acc[1] * acc[3]) / det;
+  // inliers of the current point and the normal equations; v2 repeats this refine_iters times (:171-200)
+  const int passes = p.mode == EPB_VOTE_V2 ? max(p.refine_iters, 0) : 1;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};  // a00 a01 a11 b0 b1 sum(bb^2) count
+  bool singular = false;
+  double px = win.x, py = win.y;
+  for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[i] = 0;
+    for (int t = threadIdx.x; t < tn; t += 256) {
+      const uint32_t q = __ldg(fp + t);
+      const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
+      const float2 d = __ldg(dir + t);
+      const float dx = d.x, dy = d.y;
+      if (vote_exact(cx, cy, dx, dy, dir_norm(dx, dy), win.x, win.y, p.inlier_thresh)) {
+        const double nx = dy, ny = -(double)dx;  // normal = (d_y, -d_x), :580-581
+        const double bb = nx * cx + ny * cy;
+        acc[0] += nx * nx; acc[1] += nx * ny; acc[2] += ny * ny;
+        acc[3] += nx * bb; acc[4] += ny * bb; acc[5] += bb * bb; acc[6] += 1.0;
+      }
+    }
+    block_sum_d<7>(acc, s_red);
+    const double det = acc[0] * acc[2] - acc[1] * acc[1];
+    const double tr = acc[0] + acc[2];
+    if (p.mode == EPB_VOTE_V2) {
+      // torch.pinverse semantics (:200): no inliers -> zeros (:193-195); rank-deficient normals ->
+      // minimum-norm least squares x = A^T b / ||A||_F^2; else the normal equations
+      singular = false;
+      if (acc[6] == 0.0 || !(tr > 0.0)) { px = 0.0; py = 0.0; }
+      else if (!(det > 1e-30 * tr * tr)) { px = acc[3] / tr; py = acc[4] / tr; }
+      else { px = (acc[2] * acc[3] - acc[1] * acc[4]) / det; py = (acc[0] * acc[4] - acc[1] * acc[3]) / det; }
+      win = make_float2((float)px, (float)py);
+    } else {
+      singular = !(fabs(det) > 0.0) || !isfinite(det);
+      px = NAN; py = NAN;
+      if (!singular) {
+        px = (acc[2] * acc[3] - acc[1] * acc[4]) / det;
+        py = (acc[0] * acc[4] - acc[1] * acc[3]) / det;
+      }
+    }
+    __syncthreads();   // s_red is reused by the next pass
   }
   const float fxp = (float)px, fyp = (float)py;
   if (threadIdx.x == 0) {
@@ -1127,8 +1155,8 @@ voting_for_hypothesis_kernel(const float* __restrict__ direct, const float* __re
     inliers[(size_t)hv * tn + ti] = 1;
 }
 
-// ransac_voting_kernel.cu:170-229.  Plain float arithmetic in source order (no claim of
-// bit-exactness against the reference build for this variant).
+// ransac_voting_kernel.cu:170-229 with the contraction of the reference source as built for sm_100a
+// (SASS of oracle/_ref/libref_voting.so; bitwise-checked on the GPU by tests/test_voting_gpu.py).
 __global__ void __launch_bounds__(256)
 generate_hypothesis_vp_kernel(const float* __restrict__ direct, const float* __restrict__ coords,
                               const int32_t* __restrict__ idxs, float* __restrict__ hypo, int tn,
@@ -1141,19 +1169,20 @@ generate_hypothesis_vp_kernel(const float* __restrict__ direct, const float* __r
   const float cx0 = coords[id0 * 2], cy0 = coords[id0 * 2 + 1];
   const float dx1 = direct[(size_t)id1 * vn * 2 + vi * 2], dy1 = direct[(size_t)id1 * vn * 2 + vi * 2 + 1];
   const float cx1 = coords[id1 * 2], cy1 = coords[id1 * 2 + 1];
-  const float lx0 = dy0, ly0 = -dx0, lz0 = cy0 * dx0 - cx0 * dy0;
-  const float lx1 = dy1, ly1 = -dx1, lz1 = cy1 * dx1 - cx1 * dy1;
-  float x = ly0 * lz1 - lz0 * ly1;
-  float y = lz0 * lx1 - lx0 * lz1;
-  float z = lx0 * ly1 - ly0 * lx1;
-  const float val_x0 = dx0 * (x - z * cx0), val_x1 = dx1 * (x - z * cx1);
-  const float val_y0 = dy0 * (y - z * cy0), val_y1 = dy1 * (y - z * cy1);
+  const float lz0 = __fmaf_rn(dx0, cy0, -__fmul_rn(dy0, cx0));
+  const float lz1 = __fmaf_rn(dx1, cy1, -__fmul_rn(dy1, cx1));
+  float z = __fmaf_rn(dx0, dy1, -__fmul_rn(dy0, dx1));
+  float x = __fmaf_rn(dx1, lz0, -__fmul_rn(dx0, lz1));
+  float y = __fmaf_rn(dy1, lz0, -__fmul_rn(dy0, lz1));
+  const float val_x0 = __fmul_rn(dx0, __fmaf_rn(-cx0, z, x)), val_x1 = __fmul_rn(dx1, __fmaf_rn(-cx1, z, x));
+  const float val_y0 = __fmul_rn(dy0, __fmaf_rn(-cy0, z, y)), val_y1 = __fmul_rn(dy1, __fmaf_rn(-cy1, z, y));
   if (val_x0 < 0 && val_x1 < 0 && val_y0 < 0 && val_y1 < 0) { z = -z; x = -x; y = -y; }
-  if (val_x0 * val_x1 < 0 || val_y0 * val_y1 < 0) { x = 0.f; y = 0.f; z = 0.f; }
+  if (__fmul_rn(val_x0, val_x1) < 0 || __fmul_rn(val_y0, val_y1) < 0) { x = 0.f; y = 0.f; z = 0.f; }
   hypo[hvi * 3] = x; hypo[hvi * 3 + 1] = y; hypo[hvi * 3 + 2] = z;
 }
 
-// ransac_voting_kernel.cu:268-310
+// ransac_voting_kernel.cu:268-310 as compiled: diff = fma(-c, hz, h); cosine numerator = the un-fused sum
+// of the two products the sign test reuses.
 __global__ void __launch_bounds__(256)
 voting_for_hypothesis_vp_kernel(const float* __restrict__ direct, const float* __restrict__ coords,
                                 const float* __restrict__ hypo, uint8_t* __restrict__ inliers, int tn,
@@ -1165,12 +1194,12 @@ voting_for_hypothesis_vp_kernel(const float* __restrict__ direct, const float* _
   const float cx = coords[ti * 2], cy = coords[ti * 2 + 1];
   const float hx = hypo[hv * 3], hy = hypo[hv * 3 + 1], hz = hypo[hv * 3 + 2];
   const float ddx = direct[(size_t)ti * vn * 2 + vi * 2], ddy = direct[(size_t)ti * vn * 2 + vi * 2 + 1];
-  const float fx = hx - cx * hz, fy = hy - cy * hz;
-  const float norm1 = __fsqrt_rn(ddx * ddx + ddy * ddy);
-  const float norm2 = __fsqrt_rn(fx * fx + fy * fy);
+  const float fx = __fmaf_rn(-cx, hz, hx), fy = __fmaf_rn(-cy, hz, hy);
+  const float norm1 = __fsqrt_rn(__fmaf_rn(ddx, ddx, __fmul_rn(ddy, ddy)));
+  const float norm2 = __fsqrt_rn(__fmaf_rn(fx, fx, __fmul_rn(fy, fy)));
   if ((double)norm1 < 1e-6 || (double)norm2 < 1e-6) return;
-  const float ad = __fdiv_rn(ddx * fx + ddy * fy, norm1 * norm2);
-  const float vx = fx * ddx, vy = fy * ddy;
+  const float vx = __fmul_rn(fx, ddx), vy = __fmul_rn(fy, ddy);
+  const float ad = __fdiv_rn(__fadd_rn(vx, vy), __fmul_rn(norm1, norm2));
   if (vx < 0 || vy < 0) return;
   if (fabsf(ad) > thresh) inliers[(size_t)hv * tn + ti] = 1;
 }
@@ -1189,26 +1218,35 @@ static bool params_ok(const epb_voting_params* p) {
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->vn <= 0 || p->hn <= 0 || p->rounds <= 0) return false;
   if (p->H > 65535 || p->W > 65535) return false;
   if ((long long)p->H * p->W > 0x7fffffffLL) return false;
-  if (p->mode < EPB_VOTE_V3 || p->mode > EPB_VOTE_DISTRIBUTION_WITH_MEAN) return false;
+  if (p->mode < EPB_VOTE_V3 || p->mode > EPB_VOTE_V2) return false;
+  if (p->classes < 0 || (long long)p->B * (p->classes < 1 ? 1 : p->classes) > 65535) return false;
+  if (p->mask_mode < EPB_MASK_NONZERO || p->mask_mode > EPB_MASK_CLASS) return false;
   if (p->rng_mode < EPB_RNG_IDXS || p->rng_mode > EPB_RNG_PHILOX) return false;
   if (p->stage < EPB_STAGE_ALL || p->stage > EPB_STAGE_VOTE) return false;
   if ((long long)p->hn * p->rounds > (1 << 24)) return false;
   return true;
 }
 
+// classes (image, class) pairs per image become one virtual batch (see mask_pred)
+static epb_voting_params virtual_batch(epb_voting_params p) {
+  if (p.classes < 1) p.classes = 1;
+  p.B *= p.classes;
+  return p;
+}
+
 extern "C" size_t epb_voting_workspace_bytes(const epb_voting_params* p) {
   if (!params_ok(p)) return 0;
-  return carve(*p, nullptr).bytes;
+  return carve(virtual_batch(*p), nullptr).bytes;
 }
 
 extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* io, void* workspace,
                               size_t workspace_bytes, void* stream) {
   if (!params_ok(pp) || !io || !workspace) return EPB_ERR_INVALID;
-  const epb_voting_params p = *pp;
+  const epb_voting_params p = virtual_batch(*pp);
   if (p.stage != EPB_STAGE_VOTE && (!io->mask || !io->vertex)) return EPB_ERR_INVALID;
   if (p.rng_mode != EPB_RNG_PHILOX && !io->idxs) return EPB_ERR_INVALID;
-  const bool is_layer = p.mode <= EPB_VOTE_V5;
-  const bool is_dist = p.mode >= EPB_VOTE_DISTRIBUTION;
+  const bool is_layer = p.mode <= EPB_VOTE_V5 || p.mode == EPB_VOTE_V1 || p.mode == EPB_VOTE_V2;
+  const bool is_dist = p.mode == EPB_VOTE_DISTRIBUTION || p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN;
   if (p.stage != EPB_STAGE_GATHER) {   // the gather half produces nothing but the workspace
     if (is_layer && !io->pts) return EPB_ERR_INVALID;
     if ((p.mode == EPB_VOTE_V4 || p.mode == EPB_VOTE_V5) && !io->var_or_conf) return EPB_ERR_INVALID;
@@ -1238,7 +1276,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
 
   if (p.stage != EPB_STAGE_VOTE) {
   prof_begin(PROF_COMPACT, s);
-  mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 0, ws, sc);
+  mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, p.classes, 0, ws, sc);
   EPB_RETURN_IF(check_launch());
   mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 0, p.min_num, p.max_num, allow_sub, ws);
   EPB_RETURN_IF(check_launch());
@@ -1246,7 +1284,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
                                       io->philox_consumed, io->philox_state);
   EPB_RETURN_IF(check_launch());
   if (allow_sub) {
-    mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, 1, ws, sc);
+    mask_count_kernel<<<dim3(T, p.B), 256, 0, s>>>(io->mask, HW, T, p.mask_mode, p.classes, 1, ws, sc);
     EPB_RETURN_IF(check_launch());
     mask_scan_kernel<<<p.B, 256, 0, s>>>(T, 1, p.min_num, p.max_num, allow_sub, ws);
     EPB_RETURN_IF(check_launch());

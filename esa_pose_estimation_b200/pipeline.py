@@ -71,6 +71,20 @@ class _HostPipe:
         self.turn = 0
 
 
+def poses_from_vertex_uncertainty(mask, vertex, p3d_model, K, round_hyp_num=256, min_hyp_num=4096, topk=128,
+                                  inlier_thresh=0.99, min_num=5, max_num=30000, **kw):
+    """PVNet's uncertainty-driven path (estimate_voting_distribution -> inv(sqrtm(cov)) weights ->
+    uncertainty PnP; ransac_voting_gpu.py:263-331, evaluation_utils.py:165-188), batched on the device.
+    -> dict(rt34 [B,3,4], rt6, pose7, mean, cov, weights)."""
+    mean, cov = _voting.estimate_voting_distribution(mask, vertex, round_hyp_num=round_hyp_num,
+                                                     min_hyp_num=min_hyp_num, topk=topk, inlier_thresh=inlier_thresh,
+                                                     min_num=min_num, max_num=max_num, **kw)
+    rt34, rt6, iters, cost = _pnp.uncertainty_pnp_batch(mean, cov, p3d_model, K, return_info=True)
+    pose7, _ = _pnp.pose_pack(rt6)
+    return dict(rt34=rt34, rt6=rt6, pose7=pose7, mean=mean, cov=cov, weights=_pnp.cov_to_weights(cov),
+                lm_iters=iters, lm_cost=cost)
+
+
 _host_pipes = {}
 
 

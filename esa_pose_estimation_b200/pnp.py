@@ -127,6 +127,34 @@ def esa_score(pose7_pred, pose7_gt):
     return st_, sr_
 
 
+def cov_to_weights(cov):
+    """evaluation_utils.py:170-181 on the device: cov [...,2,2] f32 -> weights [...,3] f64
+    (wxx,wxy,wyy) = inv(sqrtm(cov)); zeros for degenerate covariances."""
+    cov = cov.to(torch.float32).contiguous()
+    n = cov.numel() // 4
+    w = torch.empty(cov.shape[:-2] + (3,), dtype=torch.float64, device=cov.device)
+    with torch.cuda.device(cov.device):
+        _lib.check(_lib.load().epb_cov_to_weights(_lib.ptr(cov), n, _lib.ptr(w), _lib.stream_ptr()),
+                   "epb_cov_to_weights")
+    return w
+
+
+def uncertainty_pnp_batch(mean_pts2d, covar, points_3d, K, return_info=False):
+    """Evaluator.evaluate_uncertainty (evaluation_utils.py:165-188) batched and device-resident:
+    mean_pts2d [B,n,2], covar [B,n,2,2] (estimate_voting_distribution output), points_3d [n,3] | [B,n,3],
+    K [3,3] | [B,3,3] -> rt34 [B,3,4] f64.  The reference initialises the LM with cv2's P3P on the four
+    best-weighted points (extend_utils.py:85-89, third-party); here RANSAC-EPnP on all points gives the
+    initial pose -- both lie in the basin of the same weighted-reprojection minimiser."""
+    dev = mean_pts2d.device
+    w = cov_to_weights(covar)
+    p2, p3, Kd = _f64(mean_pts2d, dev), _f64(points_3d, dev), _f64(K, dev)
+    init = rt34_to_rt6(pnp_batch(p3, p2, Kd))
+    res = lm_refine_batch(p2, p3, w, Kd, init, return_info=return_info)
+    rt6 = res[0] if return_info else res
+    _, rt34 = pose_pack(rt6)
+    return (rt34, rt6) + tuple(res[1:]) if return_info else rt34
+
+
 # ------------------------------------------------------------------------------------ drop-ins
 def pnp(points_3d, points_2d, camera_matrix, method=SOLVEPNP_ITERATIVE):
     """pnp.py:46-90: RANSAC-EPnP (reprojectionError 5 px) -> [3,4] float64 [R|t].

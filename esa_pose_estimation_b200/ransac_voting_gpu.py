@@ -2,6 +2,7 @@
 ``lib/ransac_voting_gpu_layer/ransac_voting_gpu.py`` drivers, batched on the device.
 
 Same positional signatures and defaults as the reference:
+  ransac_voting_layer (:10)       ransac_voting_layer_v2 (:99)    (multi-class)
   ransac_voting_layer_v3 (:514)   ransac_voting_layer_v4 (:669)   ransac_voting_layer_v5 (:763)
   ransac_voting_hypothesis (:218) estimate_voting_distribution (:263)
   estimate_voting_distribution_with_mean (:333)      vertex_layer_reshape (base_utils.py:311)
@@ -65,7 +66,7 @@ def _rng_layout(numel, props):
 
 def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_in=None, idxs=None,
          raw32=False, selection=None, sync_rng=True, want_hyp=False, want_status=False,
-         stage=_lib.STAGE_ALL, workspace=None, rng_state=None):
+         stage=_lib.STAGE_ALL, workspace=None, rng_state=None, classes=1, refine_iters=1):
     """One epb_voting_run.  `stage` / `workspace` split a run in two stream-ordered halves
     (STAGE_GATHER fills `workspace`, STAGE_VOTE consumes it; same arguments both times) so that
     pipeline.py can overlap the PCIe read of one batch chunk with the voting of the previous one.
@@ -89,16 +90,20 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
     if vertex.dim() != 5 or vertex.shape[-1] != 2:
         raise RuntimeError("vertex must be [b,h,w,vn,2]")
     b, h, w, vn, _ = vertex.shape
-    mask_mode = _lib.MASK_NONZERO if mode <= _lib.VOTE_V5 else _lib.MASK_EQ1
-    mask_u8 = _mask_u8(mask, mask_mode)
+    multi = mode in (_lib.VOTE_V1, _lib.VOTE_V2)
+    mask_mode = _lib.MASK_CLASS if multi else (_lib.MASK_NONZERO if mode <= _lib.VOTE_V5 else _lib.MASK_EQ1)
+    mask_u8 = mask.to(torch.uint8).contiguous() if multi else _mask_u8(mask, mask_mode)   # class labels (mask == k+1, :25)
     assert mask_u8.shape == (b, h, w), "mask must be [b,h,w]"
     hn_total = hn * rounds
+    classes = max(int(classes), 1) if multi else 1
+    bv = b * classes                                      # (image, class) pairs: one virtual image each
 
     p = _lib.VotingParams()
     p.mode, p.B, p.H, p.W, p.vn, p.hn, p.rounds = mode, b, h, w, vn, int(hn), int(rounds)
     p.inlier_thresh, p.min_num, p.max_num, p.topk, p.mask_mode = float(thresh), int(min_num), int(max_num), int(topk), mask_mode
     sb, sy, sx, sv, sc = vertex.stride()
     p.sb, p.sy, p.sx, p.sv, p.sc = sb, sy, sx, sv, sc
+    p.classes, p.refine_iters = classes, int(refine_iters)
     props = torch.cuda.get_device_properties(dev)
     p.philox_sm_count = props.multi_processor_count
     p.philox_threads_per_sm = props.max_threads_per_multi_processor
@@ -112,7 +117,7 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
             # raw32: keep the low 32 bits (bit pattern); indices: plain conversion
             idxs = (idxs & 0xFFFFFFFF).to(torch.int64).to(torch.int32) if raw32 else idxs.to(torch.int32)
         idxs = idxs.contiguous()
-        assert idxs.numel() == b * rounds * hn * vn * 2, "idxs must be [b,rounds,hn,vn,2]"
+        assert idxs.numel() == bv * rounds * hn * vn * 2, "idxs must be [b(*classes),rounds,hn,vn,2]"
         p.rng_mode = _lib.RNG_RAW32 if raw32 else _lib.RNG_IDXS
         io.idxs = _lib.ptr(idxs)
         keep.append(idxs)
@@ -142,15 +147,18 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
         mode_outputs = False
     else:
         mode_outputs = True
-    if mode_outputs and mode <= _lib.VOTE_V5:
+    if mode_outputs and multi:
+        out["pts"] = torch.empty((b, classes, vn, 2), **f32)
+        io.pts = _lib.ptr(out["pts"])
+    elif mode_outputs and mode <= _lib.VOTE_V5:
         out["pts"] = torch.empty((b, vn, 2), **f32)
         io.pts = _lib.ptr(out["pts"])
         if mode != _lib.VOTE_V3:
             out["aux"] = torch.empty((b, vn), **f32)
             io.var_or_conf = _lib.ptr(out["aux"])
     if mode_outputs and (mode == _lib.VOTE_HYPOTHESIS or want_hyp):
-        out["hyp"] = torch.empty((b, hn_total, vn, 2), **f32)
-        out["counts"] = torch.empty((b, hn_total, vn), dtype=torch.int32, device=dev)
+        out["hyp"] = torch.empty((bv, hn_total, vn, 2), **f32)
+        out["counts"] = torch.empty((bv, hn_total, vn), dtype=torch.int32, device=dev)
         io.hyp, io.counts = _lib.ptr(out["hyp"]), _lib.ptr(out["counts"])
     if mode_outputs and mode >= _lib.VOTE_DISTRIBUTION:
         out["mean"] = torch.empty((b, vn, 2), **f32)
@@ -161,10 +169,10 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
             io.mean_in = _lib.ptr(mean_in)
             keep.append(mean_in)
     if mode_outputs:
-        out["tn"] = torch.empty((b,), dtype=torch.int32, device=dev)
+        out["tn"] = torch.empty((bv,), dtype=torch.int32, device=dev)
         io.tn_out = _lib.ptr(out["tn"])
     if want_status and mode_outputs:
-        out["status"] = torch.zeros((b, vn), dtype=torch.int32, device=dev)
+        out["status"] = torch.zeros((bv, vn), dtype=torch.int32, device=dev)
         io.status = _lib.ptr(out["status"])
     consumed = None
     if gen is not None:
@@ -193,7 +201,7 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
             gen.set_offset(p.philox_offset + int(consumed.item()))
         else:
             inc = rounds * _rng_layout(hn * vn * 2, props) + (_rng_layout(h * w, props) if h * w > max_num else 0)
-            gen.set_offset(p.philox_offset + b * inc)
+            gen.set_offset(p.philox_offset + bv * inc)
     return out
 
 
@@ -206,6 +214,22 @@ def workspace_bytes(b, h, w, vn, hn, rounds=1):
     if n == 0:
         raise RuntimeError("epb_voting_workspace_bytes: invalid parameters")
     return int(n) + 256
+
+
+def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                        min_num=5, max_num=30000, **kw):
+    """:10-97, multi-class: for every image and every class k+1 in 1..class_num-1 the winning hypothesis of
+    the pixels with mask == k+1.  -> [b, class_num-1, vn, 2] (zeros where a class has < min_num pixels)."""
+    return _run(_lib.VOTE_V1, mask, vertex, round_hyp_num, 1, inlier_thresh, min_num, max_num,
+                classes=class_num - 1, **kw)["pts"]
+
+
+def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, refine_iter_num=1, **kw):
+    """:99-216: v1 followed by `refine_iter_num` least-squares refinements over the winner's inliers
+    (torch.pinverse: zeros without inliers, minimum-norm solution for parallel normals).  -> [b,cn-1,vn,2]."""
+    return _run(_lib.VOTE_V2, mask, vertex, round_hyp_num, 1, inlier_thresh, min_num, max_num,
+                classes=class_num - 1, refine_iters=refine_iter_num, **kw)["pts"]
 
 
 def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,

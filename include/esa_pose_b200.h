@@ -15,7 +15,8 @@
  *                                    ransac_voting.cpp:64,85 (-> kernels .cu:170,268)
  *   epb_voting_workspace_bytes, epb_voting_run
  *                                    ransac_voting_gpu.py:514 ransac_voting_layer_v3, :669 _v4,
- *                                    :763 _v5, :218 ransac_voting_hypothesis,
+ *                                    :763 _v5, :10 ransac_voting_layer, :99 _v2 (multi-class),
+ *                                    :218 ransac_voting_hypothesis,
  *                                    :263 estimate_voting_distribution, :333 ..._with_mean
  *                                    (whole Python driver, batched, one stream-ordered call)
  *   epb_pnp_epnp_ransac              pnp.py:46 pnp() == cv2.solvePnPRansac(EPNP, 5 px) + Rodrigues
@@ -25,6 +26,7 @@
  *   epb_pose_pipeline                val.py:172-228 per-frame glue, batched (select, un-crop,
  *                                    EPnP-RANSAC, LM, quaternion)
  *   epb_esa_score                    demo.py:295-310
+ *   epb_cov_to_weights               lib/utils/evaluation_utils.py:170-181 cov -> inv(sqrtm(cov)) weights
  */
 #ifndef ESA_POSE_B200_H_
 #define ESA_POSE_B200_H_
@@ -101,11 +103,14 @@ enum {
   EPB_VOTE_V5 = 2,           /* -> pts, conf (re-vote at 0.999) */
   EPB_VOTE_HYPOTHESIS = 3,   /* -> hyp [B,hn,vn,2], counts [B,hn,vn] */
   EPB_VOTE_DISTRIBUTION = 4, /* -> mean, cov (top-k) */
-  EPB_VOTE_DISTRIBUTION_WITH_MEAN = 5
+  EPB_VOTE_DISTRIBUTION_WITH_MEAN = 5,
+  EPB_VOTE_V1 = 6,           /* ransac_voting_layer    (:10)  multi-class, winners -> pts [B,classes,vn,2] */
+  EPB_VOTE_V2 = 7            /* ransac_voting_layer_v2 (:99)  multi-class, pinverse refinement x refine_iters */
 };
 enum {
   EPB_MASK_NONZERO = 0, /* v3/v4/v5: mask.byte() != 0 */
-  EPB_MASK_EQ1 = 1      /* hypothesis / distribution: mask == 1 */
+  EPB_MASK_EQ1 = 1,     /* hypothesis / distribution: mask == 1 */
+  EPB_MASK_CLASS = 2    /* v1/v2: mask == class, class = 1..classes (one virtual image per pair) */
 };
 enum {
   EPB_RNG_IDXS = 0,   /* hypothesis indices supplied: idxs [B,rounds,hn,vn,2] i32 (values < tn) */
@@ -143,6 +148,10 @@ typedef struct {
   int philox_sm_count;  /* multiProcessorCount torch would see (grid clamp of its RNG kernels) */
   int philox_threads_per_sm; /* maxThreadsPerMultiProcessor */
   int stage;            /* EPB_STAGE_* */
+  int classes;          /* v1/v2: class_num - 1 foreground classes (0 or 1 otherwise).  Outputs and the
+                           optional idxs / selection / tn_out / status arrays then have B*classes leading
+                           entries, ordered (image, class) like the reference's loops */
+  int refine_iters;     /* v2: refine_iter_num */
 } epb_voting_params;
 
 size_t epb_voting_workspace_bytes(const epb_voting_params* p);
@@ -201,6 +210,11 @@ int epb_lm_refine(const double* p2d, const double* p3d, int p3d_batched, const d
 int epb_pose_pack(const double* rt6, int B, float* pose7, double* rt34, void* stream);
 /* R [B,3,3] (inside rt34 [B,3,4]) -> angle-axis like cv2.Rodrigues; rt6 [B,6]. */
 int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* stream);
+
+/* lib/utils/evaluation_utils.py:170-181 (Evaluator.evaluate_uncertainty): voting covariances
+ * cov [n,2,2] f32 -> LM weights w2d [n,3] f64 = (wxx,wxy,wyy) of inv(sqrtm(cov)); zeros where
+ * cov[0][0] < 1e-6, an entry is NaN, or cov is not positive definite. */
+int epb_cov_to_weights(const float* cov, int n, double* w2d, void* stream);
 
 /* val.py:172-228 batched.  preds [B,K,2] f32 crop px, maxvals [B,K] f32, bbox_xy [B,2] f64,
  * rate [B] f64, p3d_model [K,3] f64 (shared) , Kmat [9] f64.

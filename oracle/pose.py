@@ -121,6 +121,21 @@ def frame_pose(preds, maxvals, bbox_xy, rate, points_3d, camera_k, use_ref=False
                 idxs=idxs, epnp34=pose_pred)
 
 
+def cov_to_weights(covar):
+    """lib/utils/evaluation_utils.py:170-181: per keypoint inv(sqrtm(cov)) -> [pn,3] (wxx,wxy,wyy);
+    zeros when cov[0,0] < 1e-6 or NaN."""
+    import scipy.linalg
+    covar = np.asarray(covar)
+    cov_invs = []
+    for vi in range(covar.shape[0]):
+        if covar[vi, 0, 0] < 1e-6 or np.sum(np.isnan(covar)[vi]) > 0:
+            cov_invs.append(np.zeros([2, 2]).astype(np.float32))
+            continue
+        cov_invs.append(np.linalg.inv(scipy.linalg.sqrtm(covar[vi])))
+    weights = np.asarray(cov_invs).reshape([-1, 4])
+    return weights[:, (0, 1, 3)]
+
+
 def esa_score(q_pred, t_pred, q_gt, t_gt):
     """demo.py:295-310: per-frame ||t^-t||/||t|| + 2 Re(arccos(|q^.q| + 0j))."""
     q_pred, q_gt = np.asarray(q_pred, np.float64), np.asarray(q_gt, np.float64)

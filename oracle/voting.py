@@ -49,6 +49,33 @@ def voting_for_hypothesis(direct, coords, hyp, inliers, thresh):
         ctypes.c_int(tn), ctypes.c_int(vn), ctypes.c_int(hn), ctypes.c_float(thresh))
 
 
+def generate_hypothesis_vanishing_point(direct, coords, idxs):
+    """ransac_voting.generate_hypothesis_vanishing_point (.cpp:64 -> .cu:170-229) -> [hn,vn,3]."""
+    direct = np.ascontiguousarray(direct, np.float32)
+    coords = np.ascontiguousarray(coords, np.float32)
+    idxs = np.ascontiguousarray(idxs, np.int32)
+    tn, vn, _ = direct.shape
+    hn = idxs.shape[0]
+    hyp = np.zeros((hn, vn, 3), np.float32)
+    _lib.oracle_lib().orc_generate_hypothesis_vanishing_point(
+        _lib.fptr(direct), _lib.fptr(coords), _lib.iptr(idxs), _lib.fptr(hyp),
+        ctypes.c_int(tn), ctypes.c_int(vn), ctypes.c_int(hn))
+    return hyp
+
+
+def voting_for_hypothesis_vanishing_point(direct, coords, hyp, inliers, thresh):
+    """ransac_voting.voting_for_hypothesis_vanishing_point (.cpp:85 -> .cu:268-310); writes 1s in place."""
+    direct = np.ascontiguousarray(direct, np.float32)
+    coords = np.ascontiguousarray(coords, np.float32)
+    hyp = np.ascontiguousarray(hyp, np.float32)
+    tn, vn, _ = direct.shape
+    hn = hyp.shape[0]
+    assert inliers.dtype == np.uint8 and inliers.shape == (hn, vn, tn) and inliers.flags.c_contiguous
+    _lib.oracle_lib().orc_voting_for_hypothesis_vanishing_point(
+        _lib.fptr(direct), _lib.fptr(coords), _lib.fptr(hyp), _lib.u8ptr(inliers),
+        ctypes.c_int(tn), ctypes.c_int(vn), ctypes.c_int(hn), ctypes.c_float(thresh))
+
+
 def vote_counts(direct, coords, hyp, thresh):
     """voting_for_hypothesis + torch.sum(inlier, 2) (ransac_voting_gpu.py:557-561)."""
     direct = np.ascontiguousarray(direct, np.float32)
@@ -224,6 +251,57 @@ def ransac_voting_hypothesis(mask, vertex, round_hyp_num, inlier_thresh=0.999, m
         hyps[bi] = generate_hypothesis(direct, coords, idxs)
         counts[bi] = vote_counts(direct, coords, hyps[bi], inlier_thresh)
     return hyps, counts
+
+
+def _multiclass(mask, vertex, class_num, round_hyp_num, inlier_thresh, min_num, max_num, idxs_fn, selection_fn,
+                refine_iter_num):
+    """Common body of ransac_voting_layer (:10-97) and _v2 (:99-216).  The random draws are indexed by
+    the (image, class) pair in loop order: pair index = bi * (class_num - 1) + k."""
+    b, h, w, vn, _ = vertex.shape
+    out = np.zeros((b, class_num - 1, vn, 2), np.float32)
+    for bi in range(b):
+        for k in range(class_num - 1):
+            pair = bi * (class_num - 1) + k
+            cur_mask = mask[bi] == k + 1
+            if int(cur_mask.sum()) < min_num:
+                continue
+            _, coords, direct = compact(cur_mask, vertex[bi], max_num, selection_fn, pair)
+            tn = coords.shape[0]
+            idxs = np.asarray(idxs_fn(pair, 0, round_hyp_num, vn, tn), np.int32)
+            hyp = generate_hypothesis(direct, coords, idxs)
+            counts = vote_counts(direct, coords, hyp, inlier_thresh)
+            win = np.argmax(counts, 0)                                   # first maximum (:69)
+            ratio = counts[win, np.arange(vn)].astype(np.float32) / np.float32(tn)
+            pts = np.where((ratio > 0)[:, None], hyp[win, np.arange(vn)], 0).astype(np.float32)
+            normal = np.stack([direct[:, :, 1], -direct[:, :, 0]], 2)
+            for _ in range(refine_iter_num if refine_iter_num is not None else 0):
+                inl = np.zeros((1, vn, tn), np.uint8)
+                voting_for_hypothesis(direct, coords, pts[None], inl, inlier_thresh)
+                new = np.zeros((vn, 2), np.float32)
+                for vi in range(vn):
+                    sel = inl[0, vi] != 0
+                    if not sel.any():
+                        continue                                         # zeros (:193-195)
+                    a = normal[sel, vi, :].astype(np.float64)
+                    rhs = np.sum(a * coords[sel].astype(np.float64), 1)
+                    new[vi] = (np.linalg.pinv(a) @ rhs).astype(np.float32)    # :200
+                pts = new
+            out[bi, k] = pts
+    return out
+
+
+def ransac_voting_layer(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                        min_num=5, max_num=30000, idxs_fn=None, selection_fn=None):
+    """:10-97 -> [b, class_num-1, vn, 2]."""
+    return _multiclass(mask, vertex, class_num, round_hyp_num, inlier_thresh, min_num, max_num,
+                       idxs_fn or default_idxs_fn(0), selection_fn or default_selection_fn(0), None)
+
+
+def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20,
+                           min_num=5, max_num=30000, refine_iter_num=1, idxs_fn=None, selection_fn=None):
+    """:99-216 -> [b, class_num-1, vn, 2]."""
+    return _multiclass(mask, vertex, class_num, round_hyp_num, inlier_thresh, min_num, max_num,
+                       idxs_fn or default_idxs_fn(0), selection_fn or default_selection_fn(0), refine_iter_num)
 
 
 def _distribution_inputs(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num,

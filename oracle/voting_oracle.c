@@ -97,10 +97,11 @@ void orc_vote_counts(const float* direct, const float* coords, const float* hypo
     }
 }
 
-/* ransac_voting_kernel.cu:170-229 (vanishing-point hypothesis, homogeneous).
- * Contraction as in the shipped SASS is NOT reproduced here (plain C order with
- * -ffp-contract=off); this variant is checked against oracle/_ref with a
- * tolerance, see DESIGN.md ("next" row f4). */
+/* ransac_voting_kernel.cu:170-229 (vanishing-point hypothesis, homogeneous), with the FMA
+ * contraction nvcc 12.9 / ptxas apply to the reference source for sm_100a (SASS of
+ * oracle/_ref/libref_voting.so): lz = fma(dx, cy, -rn(dy cx)), z = fma(dx0, dy1, -rn(dy0 dx1)),
+ * x = fma(dx1, lz0, -rn(dx0 lz1)), y = fma(dy1, lz0, -rn(dy0 lz1)), x - z c = fma(-c, z, x);
+ * the two sign products are tested through one min (NaN is ignored by both forms). */
 void orc_generate_hypothesis_vanishing_point(const float* direct, const float* coords,
                                              const int* idxs, float* hypo_pts, int tn, int vn,
                                              int hn) {
@@ -112,13 +113,13 @@ void orc_generate_hypothesis_vanishing_point(const float* direct, const float* c
       const float cx0 = coords[id0 * 2], cy0 = coords[id0 * 2 + 1];
       const float dx1 = direct[id1 * vn * 2 + vi * 2], dy1 = direct[id1 * vn * 2 + vi * 2 + 1];
       const float cx1 = coords[id1 * 2], cy1 = coords[id1 * 2 + 1];
-      const float lx0 = dy0, ly0 = -dx0, lz0 = cy0 * dx0 - cx0 * dy0;
-      const float lx1 = dy1, ly1 = -dx1, lz1 = cy1 * dx1 - cx1 * dy1;
-      float x = ly0 * lz1 - lz0 * ly1;
-      float y = lz0 * lx1 - lx0 * lz1;
-      float z = lx0 * ly1 - ly0 * lx1;
-      const float val_x0 = dx0 * (x - z * cx0), val_x1 = dx1 * (x - z * cx1);
-      const float val_y0 = dy0 * (y - z * cy0), val_y1 = dy1 * (y - z * cy1);
+      const float lz0 = fmaf(dx0, cy0, -(dy0 * cx0));
+      const float lz1 = fmaf(dx1, cy1, -(dy1 * cx1));
+      float z = fmaf(dx0, dy1, -(dy0 * dx1));
+      float x = fmaf(dx1, lz0, -(dx0 * lz1));
+      float y = fmaf(dy1, lz0, -(dy0 * lz1));
+      const float val_x0 = dx0 * fmaf(-cx0, z, x), val_x1 = dx1 * fmaf(-cx1, z, x);
+      const float val_y0 = dy0 * fmaf(-cy0, z, y), val_y1 = dy1 * fmaf(-cy1, z, y);
       if (val_x0 < 0 && val_x1 < 0 && val_y0 < 0 && val_y1 < 0) { z = -z; x = -x; y = -y; }
       if (val_x0 * val_x1 < 0 || val_y0 * val_y1 < 0) { x = 0.f; y = 0.f; z = 0.f; }
       hypo_pts[hi * vn * 3 + vi * 3] = x;
@@ -127,7 +128,8 @@ void orc_generate_hypothesis_vanishing_point(const float* direct, const float* c
     }
 }
 
-/* ransac_voting_kernel.cu:268-310. */
+/* ransac_voting_kernel.cu:268-310 as compiled: diff = fma(-c, hz, h); the numerator of the cosine is the
+ * un-fused sum of the two products that the sign test reuses. */
 void orc_voting_for_hypothesis_vanishing_point(const float* direct, const float* coords,
                                                const float* hypo_pts, uint8_t* inliers, int tn,
                                                int vn, int hn, float thresh) {
@@ -143,8 +145,8 @@ void orc_voting_for_hypothesis_vanishing_point(const float* direct, const float*
         const float norm1 = sqrtf(fmaf(ddx, ddx, ddy * ddy));
         const float norm2 = sqrtf(fmaf(fx, fx, fy * fy));
         if ((double)norm1 < 1e-6 || (double)norm2 < 1e-6) continue;
-        const float ad = (ddx * fx + ddy * fy) / (norm1 * norm2);
         const float vx = fx * ddx, vy = fy * ddy;
+        const float ad = (vx + vy) / (norm1 * norm2);
         if (vx < 0 || vy < 0) continue;
         if (fabsf(ad) > thresh) out[ti] = 1;
       }

@@ -102,3 +102,20 @@ def test_frame_pose_and_score():
     q_gt = opose.quat_wxyz_from_matrix(rodrigues(c["rvec"]))
     st, sr = opose.esa_score(out["q"], out["t"], q_gt, c["t"])
     assert st < 0.02 and sr < 0.02
+
+
+def test_cov_to_weights_oracle_matches_closed_form():
+    """evaluation_utils.py:170-181 restated with scipy's sqrtm == the 2x2 SPD closed form the kernel uses."""
+    from oracle import pose as opose
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=(40, 2, 2))
+    cov = (a @ a.transpose(0, 2, 1) + 1e-3 * np.eye(2)).astype(np.float32)
+    cov[3, 0, 0] = 1e-7                                   # guard: zero weights
+    cov[5, 1, 1] = np.nan
+    w = opose.cov_to_weights(cov)
+    assert (w[3] == 0).all() and (w[5] == 0).all()
+    for i in (0, 1, 2, 7, 20):
+        c = cov[i].astype(np.float64)
+        s = np.sqrt(np.linalg.det(c)); t = np.sqrt(np.trace(c) + 2 * s)
+        winv = np.linalg.inv((c + s * np.eye(2)) / t)
+        np.testing.assert_allclose(w[i], [winv[0, 0], winv[0, 1], winv[1, 1]], rtol=2e-4, atol=1e-6)

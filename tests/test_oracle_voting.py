@@ -121,3 +121,17 @@ def test_distribution_mean_cov():
     m2, cov2 = ov.estimate_voting_distribution_with_mean(mask, vx, mean, round_hyp_num=32, min_hyp_num=128)
     np.testing.assert_array_equal(m2, mean)
     assert np.isfinite(cov2).all()
+
+
+def test_multiclass_oracle_reduces_to_single_class():
+    """With one foreground class the multi-class drivers (:10, :99) follow the single-class v3 path:
+    same winner, and v2's pinverse refinement equals v3's normal equations."""
+    mask, vertex, kpts = make_vertex_field(5, 1, 48, 48, 3, 0.5, noise_deg=1.0)
+    vx = vertex_hwvn2(vertex)
+    fn = ov.default_idxs_fn(2)
+    v3 = ov.ransac_voting_layer_v3(mask, vx, 96, idxs_fn=fn)
+    v2 = ov.ransac_voting_layer_v2(mask, vx, 2, 96, idxs_fn=fn)
+    v1 = ov.ransac_voting_layer(mask, vx, 2, 96, idxs_fn=fn)
+    assert v2.shape == (1, 1, 3, 2) and v1.shape == (1, 1, 3, 2)
+    np.testing.assert_allclose(v2[:, 0], v3, atol=2e-3)
+    assert np.abs(v1[0, 0] - kpts[0]).max() < 3.0

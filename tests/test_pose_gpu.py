@@ -214,3 +214,32 @@ def test_lm_sweep_properties(cuda_dev):
     out2 = P.lm_refine_batch(torch.from_numpy(p2).to(cuda_dev), torch.from_numpy(model).to(cuda_dev),
                              torch.from_numpy(w).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev), out)
     assert (out2 - out).abs().max().item() < 1e-7
+
+
+def test_cov_to_weights_and_uncertainty_pnp_match_oracle(cuda_dev):
+    """f2: inv(sqrtm(cov)) weights (evaluation_utils.py:170-181) and the uncertainty PnP built on them
+    (extend_utils.py:64-115, P3P-initialised in the reference) reach the oracle's minimiser."""
+    from esa_pose_estimation_b200 import pnp as gp
+    from oracle import pose as opose
+    rng = np.random.default_rng(11)
+    B, n = 6, 9
+    model = tango_model(n, seed=4)
+    p2d = np.zeros((B, n, 2)); cov = np.zeros((B, n, 2, 2), np.float32); truth = []
+    for i in range(B):
+        c = make_pose_case(500 + i, n, 0.0, 0, model=model)
+        a = rng.normal(size=(n, 2, 2)) * rng.uniform(0.3, 2.0, (n, 1, 1))
+        cv = a @ a.transpose(0, 2, 1) + 0.05 * np.eye(2)
+        cov[i] = cv.astype(np.float32)
+        noise = np.stack([np.linalg.cholesky(cv[k]) @ rng.normal(size=2) for k in range(n)]) * 0.3
+        p2d[i] = c["p2d"] + noise
+        truth.append(c)
+    cov[2, 4, 0, 0] = 1e-7                                # a keypoint the guard switches off
+    w = gp.cov_to_weights(torch.from_numpy(cov).to(cuda_dev)).cpu().numpy()
+    for i in range(B):
+        np.testing.assert_allclose(w[i], opose.cov_to_weights(cov[i]), rtol=2e-4, atol=1e-6)
+    rt34 = gp.uncertainty_pnp_batch(torch.from_numpy(p2d).to(cuda_dev), torch.from_numpy(cov).to(cuda_dev),
+                                    torch.from_numpy(model).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev)).cpu().numpy()
+    for i in range(B):
+        ref = opose.uncertainty_pnp(p2d[i], w[i], model, ESA_K)
+        assert _ang(rt34[i, :, :3], ref[:, :3]) < 1e-3
+        assert np.linalg.norm(rt34[i, :, 3] - ref[:, 3]) / np.linalg.norm(ref[:, 3]) < 1e-4

@@ -306,3 +306,71 @@ def test_pinned_host_field_is_read_in_place(cuda_dev):
         assert torch.equal(host_out[k].view(torch.int32), dev_out[k].view(torch.int32)), k
     with pytest.raises(RuntimeError):
         rv.ransac_voting_layer_v3(m_h.to(cuda_dev), rv.vertex_layer_reshape(torch.from_numpy(vertex)), hn, idxs=i_t)
+
+
+def test_multiclass_v1_v2_match_oracle(cuda_dev):
+    """ransac_voting_layer (:10) / _v2 (:99): one voting run per (image, class) pair, mask == k+1."""
+    from esa_pose_estimation_b200 import ransac_voting_gpu as rv
+    b, h, w, vn, hn, class_num = 2, 64, 72, 4, 128, 4
+    mask, vertex, _ = make_vertex_field(81, b, h, w, vn, 0.9, noise_deg=1.0)
+    # three foreground classes as vertical bands of the ellipse; class 3 of image 1 nearly empty
+    lab = np.zeros_like(mask)
+    lab[:, :, : w // 3] = 1; lab[:, :, w // 3: 2 * w // 3] = 2; lab[:, :, 2 * w // 3:] = 3
+    mask = (mask * lab).astype(np.uint8)
+    mask[1][mask[1] == 3] = 0
+    mask[1, 5, w - 3:] = 3                                               # 3 pixels < min_num
+    vx = vertex_hwvn2(vertex)
+    classes = class_num - 1
+    fn = ov.default_idxs_fn(17)
+    idxs = np.zeros((b * classes, 1, hn, vn, 2), np.int32)
+    for bi in range(b):
+        for k in range(classes):
+            tn = int((mask[bi] == k + 1).sum())
+            if tn >= 5:
+                idxs[bi * classes + k, 0] = fn(bi * classes + k, 0, hn, vn, tn)
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev))
+    i_t = torch.from_numpy(idxs).to(cuda_dev)
+    p1 = rv.ransac_voting_layer(m_t, vert, class_num, hn, idxs=i_t).cpu().numpy()
+    p1_o = ov.ransac_voting_layer(mask, vx, class_num, hn, idxs_fn=fn)
+    assert p1.shape == (b, classes, vn, 2)
+    np.testing.assert_array_equal(p1.view(np.int32), p1_o.view(np.int32))     # winners are hypotheses: bit-exact
+    assert (p1[1, 2] == 0).all()
+    for iters in (1, 2):
+        p2 = rv.ransac_voting_layer_v2(m_t, vert, class_num, hn, refine_iter_num=iters, idxs=i_t).cpu().numpy()
+        p2_o = ov.ransac_voting_layer_v2(mask, vx, class_num, hn, refine_iter_num=iters, idxs_fn=fn)
+        np.testing.assert_allclose(p2, p2_o, rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize("kind,seed", [("structured", 4), ("randinit", 5)])
+def test_vanishing_point_primitives_bit_exact_vs_reference_kernels(cuda_dev, kind, seed):
+    """ransac_voting_kernel.cu:170-229 / :268-310 (homogeneous hypotheses): ours and the C restatement
+    against the reference's own kernels compiled for sm_100a, bitwise."""
+    from esa_pose_estimation_b200 import ransac_voting
+    ref = _ref_lib()
+    coords, direct = _compact_case(seed, 40, 48, 4, 0.7, kind)
+    tn, vn, _ = direct.shape
+    hn = 80
+    rng = np.random.default_rng(seed)
+    idxs = rng.integers(0, tn, (hn, vn, 2)).astype(np.int32)
+    idxs[0, :, 1] = idxs[0, :, 0]                                      # the same ray twice
+    d_t, c_t, i_t = (torch.from_numpy(a).to(cuda_dev) for a in (direct, coords, idxs))
+    hyp_ref = torch.zeros((hn, vn, 3), device=cuda_dev)
+    assert ref.ref_generate_hypothesis_vanishing_point(_dp(d_t), _dp(c_t), _dp(i_t), _dp(hyp_ref), tn, vn, hn) == 0
+    torch.cuda.synchronize()
+    hyp = ransac_voting.generate_hypothesis_vanishing_point(d_t, c_t, i_t)
+    assert torch.equal(hyp.view(torch.int32), hyp_ref.view(torch.int32))
+    hyp_c = ov.generate_hypothesis_vanishing_point(direct, coords, idxs)
+    np.testing.assert_array_equal(hyp_c.view(np.int32), hyp_ref.cpu().numpy().view(np.int32))
+    assert (hyp_ref != 0).any()
+    for thresh in (0.999, 0.99, 0.5):
+        inl_ref = torch.zeros((hn, vn, tn), dtype=torch.uint8, device=cuda_dev)
+        assert ref.ref_voting_for_hypothesis_vanishing_point(_dp(d_t), _dp(c_t), _dp(hyp_ref), _dp(inl_ref), tn, vn, hn,
+                                                             ctypes.c_float(thresh)) == 0
+        torch.cuda.synchronize()
+        inl = torch.zeros((hn, vn, tn), dtype=torch.uint8, device=cuda_dev)
+        ransac_voting.voting_for_hypothesis_vanishing_point(d_t, c_t, hyp_ref, inl, thresh)
+        assert torch.equal(inl, inl_ref)
+        inl_c = np.zeros((hn, vn, tn), np.uint8)
+        ov.voting_for_hypothesis_vanishing_point(direct, coords, hyp_ref.cpu().numpy(), inl_c, thresh)
+        np.testing.assert_array_equal(inl_c, inl_ref.cpu().numpy())

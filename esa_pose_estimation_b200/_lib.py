@@ -51,6 +51,7 @@ SIGNATURES = {
     "epb_profile_read": (c_int, [c_int, ctypes.POINTER(c_double), ctypes.POINTER(c_int)]),
     "epb_decode_heatmaps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "epb_refine_keypoints": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "epb_refine_keypoints_dark": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "epb_generate_hypothesis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "epb_voting_for_hypothesis": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "epb_generate_hypothesis_vanishing_point": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -150,6 +150,97 @@ __global__ void refine_keypoints_kernel(const float* __restrict__ hm, int n_maps
   }
 }
 
+// inference.py:154-170 get_final2 (DARK-style decode) on caller-supplied integer peaks:
+//   gaussian_blur(hm, 11) (:96-110: zero-padded copy in float64, cv2.GaussianBlur(11x11, sigma from the
+//   kernel size = 2.0), cast back to float32, rescaled so that the map keeps its maximum),
+//   clip at 1e-10, float32 log, then taylor (:54-73): full 2x2 Hessian Newton step at the peak,
+//   applied whenever the Hessian determinant is non-zero.
+// One CTA per map.  The whole map has to be blurred because the rescale needs the maximum of the
+// BLURRED map; it is streamed through shared memory in row bands (separable 11-tap filter, float64
+// like cv2 on the float64 copy), HBM traffic = one read of the map.
+struct GaussKernel11 { double k[6]; };  // k[0] centre, k[i] = k[-i]
+
+__global__ void __launch_bounds__(256)
+dark_refine_kernel(const float* __restrict__ hm, int n_maps, int H, int W, int band_rows, GaussKernel11 g,
+                   float* __restrict__ xy) {
+  extern __shared__ __align__(16) unsigned char dark_smem[];
+  const int map = blockIdx.x;
+  const float* p = hm + (size_t)map * H * W;
+  const int rows = band_rows + 10;
+  double* tmp = reinterpret_cast<double*>(dark_smem);                 // [rows][W] horizontally blurred
+  float* in = reinterpret_cast<float*>(dark_smem + (size_t)rows * W * 8);  // [rows][W]
+  __shared__ float s_st[5][5];
+  __shared__ float s_red[2][8];
+  const float fx0 = xy[2 * map], fy0 = xy[2 * map + 1];
+  const int px = (int)fx0, py = (int)fy0;
+  float omax = -INFINITY, bmax = -INFINITY;
+  for (int r0 = 0; r0 < H; r0 += band_rows) {
+    for (int e = threadIdx.x; e < rows * W; e += 256) {
+      const int rr = e / W, c = e - rr * W;
+      const int r = r0 - 5 + rr;
+      float v = 0.f;
+      if (r >= 0 && r < H) {
+        v = __ldg(p + (size_t)r * W + c);
+        if (rr >= 5 && rr < 5 + band_rows) omax = fmaxf(omax, v);
+      }
+      in[e] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < rows * W; e += 256) {
+      const int rr = e / W, c = e - rr * W;
+      const float* row = in + rr * W;
+      double acc = g.k[0] * (double)row[c];
+#pragma unroll
+      for (int i = 1; i <= 5; ++i) {
+        const double a = c - i >= 0 ? (double)row[c - i] : 0.0, b = c + i < W ? (double)row[c + i] : 0.0;
+        acc += g.k[i] * (a + b);
+      }
+      tmp[e] = acc;
+    }
+    __syncthreads();
+    const int nb = min(band_rows, H - r0);
+    for (int e = threadIdx.x; e < nb * W; e += 256) {
+      const int rr = e / W, c = e - rr * W;
+      const double* col = tmp + (size_t)(rr + 5) * W + c;
+      double acc = g.k[0] * col[0];
+#pragma unroll
+      for (int j = 1; j <= 5; ++j) acc += g.k[j] * (col[-j * W] + col[j * W]);
+      const float v = (float)acc;
+      bmax = fmaxf(bmax, v);
+      const int r = r0 + rr;
+      if (r >= py - 2 && r <= py + 2 && c >= px - 2 && c <= px + 2) s_st[r - py + 2][c - px + 2] = v;
+    }
+    __syncthreads();
+  }
+  omax = fmaxf(omax, __shfl_xor_sync(FULL, omax, 16)); bmax = fmaxf(bmax, __shfl_xor_sync(FULL, bmax, 16));
+#pragma unroll
+  for (int m = 8; m > 0; m >>= 1) {
+    omax = fmaxf(omax, __shfl_xor_sync(FULL, omax, m)); bmax = fmaxf(bmax, __shfl_xor_sync(FULL, bmax, m));
+  }
+  if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = omax; s_red[1][threadIdx.x >> 5] = bmax; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  for (int w = 0; w < 8; ++w) { omax = fmaxf(omax, s_red[0][w]); bmax = fmaxf(bmax, s_red[1][w]); }
+  if (!(px > 1 && px < W - 2 && py > 1 && py < H - 2)) return;       // inference.py:59
+  const float scale = __fdiv_rn(omax, bmax);                            // hm *= origin_max / np.max(hm), float32
+  auto L = [&](int dy, int dx) { return logf(fmaxf(__fmul_rn(s_st[dy + 2][dx + 2], scale), 1e-10f)); };
+  const float c0 = L(0, 0);
+  const float dx = 0.5f * (L(0, 1) - L(0, -1));
+  const float dy = 0.5f * (L(1, 0) - L(-1, 0));
+  const float dxx = 0.25f * (L(0, 2) - 2.f * c0 + L(0, -2));
+  const float dxy = 0.25f * (L(1, 1) - L(-1, 1) - L(1, -1) + L(-1, -1));
+  const float dyy = 0.25f * (L(2, 0) - 2.f * c0 + L(-2, 0));
+  const float det = __fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy));
+  if (det != 0.f) {
+    // offset = -inv(hessian) derivative (numpy.linalg.inv on float32; evaluated here in float64)
+    const double d = (double)dxx * dyy - (double)dxy * dxy;
+    const float ox = (float)(-((double)dyy * dx - (double)dxy * dy) / d);
+    const float oy = (float)(-((double)dxx * dy - (double)dxy * dx) / d);
+    xy[2 * map] = fx0 + ox;
+    xy[2 * map + 1] = fy0 + oy;
+  }
+}
+
 }  // namespace epb
 
 extern "C" int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, int flags, float* xy,
@@ -174,5 +265,32 @@ extern "C" int epb_refine_keypoints(const float* hm, int n_maps, int H, int W, f
   if (!hm || !xy || n_maps < 0 || H <= 0 || W <= 0) return EPB_ERR_INVALID;
   if (n_maps == 0) return EPB_OK;
   refine_keypoints_kernel<<<(n_maps + 127) / 128, 128, 0, (cudaStream_t)stream>>>(hm, n_maps, H, W, xy);
+  return check_launch();
+}
+
+extern "C" int epb_refine_keypoints_dark(const float* hm, int n_maps, int H, int W, float* xy, void* stream) {
+  using namespace epb;
+  if (!hm || !xy || n_maps < 0 || H <= 0 || W <= 0 || W > 4096) return EPB_ERR_INVALID;
+  if (n_maps == 0) return EPB_OK;
+  // cv2.getGaussianKernel(11, sigma <= 0): sigma = 0.3*((11-1)*0.5 - 1) + 0.8 = 2.0, normalised to sum 1
+  GaussKernel11 g;
+  {
+    const double sigma = 0.3 * ((11 - 1) * 0.5 - 1) + 0.8, scale2x = -0.5 / (sigma * sigma);
+    double cf[11], sum = 0;
+    for (int i = 0; i < 11; ++i) { const double x = i - 5; cf[i] = exp(scale2x * x * x); sum += cf[i]; }
+    for (int i = 0; i <= 5; ++i) g.k[i] = cf[5 + i] * (1.0 / sum);
+  }
+  int band = (int)(200 * 1024 / ((size_t)W * 12)) - 10;
+  if (band > H) band = H;
+  if (band > 64) band = 64;
+  if (band < 1) return EPB_ERR_INVALID;
+  const size_t smem = (size_t)(band + 10) * W * 12;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(dark_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+      return check_api(cudaGetLastError());
+    attr_set = true;
+  }
+  dark_refine_kernel<<<n_maps, 256, smem, (cudaStream_t)stream>>>(hm, n_maps, H, W, band, g, xy);
   return check_launch();
 }

@@ -1,7 +1,7 @@
 """Heatmap decoding -- drop-in for the reference's ``inference.py`` on the CUDA path.
 
 Same names, argument meaning and return values as /root/reference/inference.py:
-``get_max_preds`` (:22), ``get_final`` (:136), ``getPrediction`` (:171); plus the batched
+``get_max_preds`` (:22), ``get_final`` (:136), ``get_final2`` (:154), ``getPrediction`` (:171); plus the batched
 device-resident entry ``decode_heatmaps`` that replaces the per-frame two-stage ``torch.max``
 and 150 ``.item()`` syncs of val.py:151-166.  Everything computes in
 csrc/decode.cu through the C ABI; there is no CPU fallback.
@@ -60,6 +60,29 @@ def get_final(hm, coords):
     st = _lib.load().epb_refine_keypoints(_lib.ptr(hm_t), min(n, k), h, w, _lib.ptr(xy), _lib.stream_ptr())
     _lib.check(st, "epb_refine_keypoints")
     out = xy.cpu().numpy()
+    for p in range(n):
+        coords[p] = out[p]
+    return out.copy() if isinstance(coords, list) else coords.copy()
+
+
+def refine_dark(hms, xy):
+    """Batched get_final2 on the device: hms [B,K,H,W] CUDA f32, xy [B,K,2] f32 integer peaks -> refined copy."""
+    hms = hms.contiguous()
+    b, k, h, w = hms.shape
+    out = xy.to(torch.float32).contiguous().clone()
+    with torch.cuda.device(hms.device):
+        st = _lib.load().epb_refine_keypoints_dark(_lib.ptr(hms), b * k, h, w, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(st, "epb_refine_keypoints_dark")
+    return out
+
+
+def get_final2(hm, coords):
+    """inference.py:154-170 (DARK-style decode).  hm numpy [1,K,H,W]; coords: K float32[2] integer peaks,
+    mutated in place like the reference; returns the refined [K,2] array."""
+    hm_t = torch.from_numpy(np.ascontiguousarray(hm[:1], dtype=np.float32)).to(_device())
+    n = len(coords)
+    xy = torch.from_numpy(np.ascontiguousarray(np.asarray(coords, dtype=np.float32).reshape(1, n, 2))).to(hm_t.device)
+    out = refine_dark(hm_t[:, :n], xy)[0].cpu().numpy()
     for p in range(n):
         coords[p] = out[p]
     return out.copy() if isinstance(coords, list) else coords.copy()

@@ -8,6 +8,7 @@
  *
  *   epb_decode_heatmaps              inference.py:22 get_max_preds, :136 get_final (+ :75 my_taylor),
  *                                    :171 getPrediction; val.py:151-164 two-stage torch.max
+ *   epb_refine_keypoints_dark        inference.py:154 get_final2 (:96 gaussian_blur, :54 taylor)
  *   epb_generate_hypothesis          lib/ransac_voting_gpu_layer/src/ransac_voting.cpp:20
  *                                    (pybind ransac_voting.generate_hypothesis -> kernel .cu:11)
  *   epb_voting_for_hypothesis        ransac_voting.cpp:41 (-> kernel .cu:88)
@@ -78,6 +79,11 @@ int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, int flags, fl
 /* inference.py:136 get_final on caller-supplied peaks: xy [n_maps,2] f32 in/out (the integer part
  * of each coordinate selects the stencil centre, exactly like int(coord[0]) at inference.py:79). */
 int epb_refine_keypoints(const float* hm, int n_maps, int H, int W, float* xy, void* stream);
+
+/* inference.py:154 get_final2 (DARK-style decode: 11x11 Gaussian blur of the whole map, renormalised to
+ * its maximum, float32 log, full 2x2 Hessian Newton step of inference.py:54 taylor) on caller-supplied
+ * peaks: xy [n_maps,2] f32 in/out. */
+int epb_refine_keypoints_dark(const float* hm, int n_maps, int H, int W, float* xy, void* stream);
 
 /* ------------------------------------------------- pybind-level voting primitives (a9,a10,a21) */
 /* direct [tn,vn,2] f32, coords [tn,2] f32, idxs [hn,vn,2] i32 -> hypo [hn,vn,2] f32.

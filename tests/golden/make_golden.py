@@ -36,8 +36,12 @@ def decode_cases():
         final = ref_inference.get_final(hm.copy(), co)
         import torch
         gp, gm = ref_inference.getPrediction(torch.from_numpy(hm.copy()))
+        # DARK-style decode, inference.py:154-170 (np.matrix and all): same integer peaks
+        co2 = [preds[0, i].copy() for i in range(k)]
+        final2 = ref_inference.get_final2(hm.copy(), co2)
         np.savez_compressed(os.path.join(HERE, "decode_%s.npz" % name), hm=hm, preds=preds, maxvals=maxvals,
-                            final=np.asarray(final, np.float32), getpred=gp.numpy(), getpred_max=gm.numpy())
+                            final=np.asarray(final, np.float32), getpred=gp.numpy(), getpred_max=gm.numpy(),
+                            final2=np.asarray(final2, np.float32))
         print("decode", name, hm.shape, float(np.abs(np.asarray(final) - preds[0]).max()))
 
 

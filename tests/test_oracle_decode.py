@@ -30,6 +30,10 @@ def test_oracle_matches_reference(golden_dir, name):
     gp, gm = odec.get_prediction(hm)
     np.testing.assert_array_equal(gp, g["getpred"])
     np.testing.assert_array_equal(gm, g["getpred_max"])
+    # DARK-style decode (inference.py:154-170): np.matrix in the reference, plain arrays here
+    co2 = [g["preds"][0, i].copy() for i in range(hm.shape[1])]
+    final2 = odec.get_final2(hm.copy(), co2)
+    np.testing.assert_allclose(np.asarray(final2, np.float32), g["final2"], rtol=0, atol=1e-5)
 
 
 def test_select_keypoints_ties_and_floor():

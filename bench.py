@@ -154,7 +154,10 @@ def run_reference(a):
 
 # ----------------------------------------------------------------------------- our arm
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """One `nvidia-smi -lms` process for the whole run, started BEFORE the warm-up (its start-up takes
+    driver locks for a few hundred ms and must not fall into a timed region); samples carry wall-clock
+    timestamps and are attributed to the timed regions afterwards."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -167,11 +170,19 @@ class ClockSampler:
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        self.rows = None
+
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.02)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
-            return out
+            self.rows = []
+            return
         time.sleep(0.05)
         self.p.terminate()
         try:
@@ -179,25 +190,38 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush(); self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         for ln in self.f.read().strip().splitlines():
             c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
+            if len(c) < 8:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), [n for n, v in zip(
+                    ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8])
+                    if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        self.rows = rows
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+
+    def region(self, t0, t1):
+        """Clocks line for the samples taken in [t0, t1] (wall clock); falls back to the nearest sample
+        when the region is shorter than the sampling period."""
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.rows:
+            return out
+        sel = [r for r in self.rows if t0 - 0.005 <= r[0] <= t1 + 0.005]
+        if not sel:
+            mid = 0.5 * (t0 + t1)
+            sel = [min(self.rows, key=lambda r: abs(r[0] - mid))]
+            out["note"] = "region shorter than the 20 ms sampling period: nearest sample"
+        out.update(sm_mhz=float(np.median([r[1] for r in sel])), sm_max_mhz=float(max(r[2] for r in sel)),
+                   reasons=sorted({x for r in sel for x in r[3]}), samples=len(sel))
         return out
 
 
@@ -269,6 +293,9 @@ def run_ours(a):
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("EPB_NO_SAMPLER") else None
+    if sampler:
+        sampler.wait_first_sample()
     for _ in range(max(a.warmup, 3)):
         last = step_device()
     barrier()
@@ -277,10 +304,11 @@ def run_ours(a):
     kerr = float((step_device.kpts.double().cpu() - torch.from_numpy(kcrop_np)).abs().max())
     assert kerr < 1.0, "voting did not recover the planted keypoints (max err %.3f px)" % kerr
 
-    sampler = ClockSampler(local) if rank == 0 else None
     lib.epb_profile_enable(1)
     launches0 = lib.epb_launch_count()
+    t_dev0 = time.time()
     ms_dev = timed(step_device, a.steps)
+    t_dev1 = time.time()
     launches = lib.epb_launch_count() - launches0
     prof = {}
     for cls, name in ((0, "compaction"), (1, "hypothesis"), (2, "vote_count"), (3, "winner_refine"), (4, "pose")):
@@ -288,13 +316,16 @@ def run_ours(a):
         lib.epb_profile_read(cls, tot, n)
         prof[name] = (tot.value, n.value)
     lib.epb_profile_enable(0)
-    clocks = sampler.stop() if sampler else None
 
     for _ in range(max(a.warmup, 3)):
         step_e2e()
-    sampler2 = ClockSampler(local) if rank == 0 else None
+    t_e0 = time.time()
     ms_e2e = timed(step_e2e, a.steps)
-    clocks_e2e = sampler2.stop() if sampler2 else None
+    t_e1 = time.time()
+    clocks = clocks_e2e = None
+    if sampler:
+        sampler.stop()
+        clocks, clocks_e2e = sampler.region(t_dev0, t_dev1), sampler.region(t_e0, t_e1)
 
     if rank != 0:
         if world > 1:

@@ -44,8 +44,11 @@ def poses_from_vertex(mask, vertex, p3d_model, K, round_hyp_num=512, inlier_thre
     -> dict(pose7, rt6, epnp_rt34, status, kpts).
 
     `vertex` (and `mask`) may live in PINNED host memory.  The batch is then cut into `chunks`
-    pieces (default 4 when B >= 16): a high-priority side stream compacts the foreground and reads
-    the field of piece i+1 in place over PCIe while the current stream votes and solves piece i."""
+    pieces (default 4 when B >= 16) and flows through three streams: a high-priority stream compacts
+    the foreground and reads the field of piece i+1 in place over PCIe while a second stream votes
+    piece i; the caller's stream waits for the keypoints and solves the poses (so the latency-bound
+    pose solve of one call also overlaps the voting of the next).  Results are valid on the caller's
+    stream, as usual."""
     host = isinstance(vertex, torch.Tensor) and not vertex.is_cuda
     b = vertex.shape[0]
     if chunks is None:
@@ -67,7 +70,9 @@ class _HostPipe:
 
     def __init__(self, dev):
         self.gs = torch.cuda.Stream(device=dev, priority=-1)
+        self.vs = torch.cuda.Stream(device=dev)              # voting; the caller's stream only solves the poses
         self.sets = [None, None]          # each: dict(ws=[tensors], done=[events], need=int)
+        self.finished = [None, None]      # event after the pose solve of the call that last used the set
         self.turn = 0
 
 
@@ -97,13 +102,20 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
     pipe = _host_pipes.get(key)
     if pipe is None:
         pipe = _host_pipes[key] = _HostPipe(dev)
-    gs = pipe.gs
+    gs, vs = pipe.gs, pipe.vs
     bounds = [shard_range(b, i, chunks) for i in range(chunks)]
     per = max(e - s for s, e in bounds)
     need = _voting.workspace_bytes(per, h, w, vn, hn)
-    st = pipe.sets[pipe.turn]
+    turn = pipe.turn
+    # At most two calls in flight: the host waits (spinning on an event) for the call that used this
+    # workspace set two turns ago.  Without it a host that enqueues faster than the GPU drains fills the
+    # gather stream's launch queue, and the driver then parks the enqueueing thread for up to ~100 ms
+    # (measured: tools/stallhunt.py), long enough to starve the GPU.
+    if pipe.finished[turn] is not None:
+        pipe.finished[turn].synchronize()
+    st = pipe.sets[turn]
     if st is None or len(st["ws"]) < chunks or st["need"] < need:
-        st = pipe.sets[pipe.turn] = dict(
+        st = pipe.sets[turn] = dict(
             ws=[torch.empty((need,), dtype=torch.uint8, device=dev) for _ in range(chunks)],
             done=[None] * chunks, need=need)
     pipe.turn ^= 1
@@ -145,19 +157,29 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
             events.append(ev)
             masks_d.append(m_d)
     kps = []
-    for i, (s, e) in enumerate(bounds):
-        cur.wait_event(events[i])
-        kps.append(_voting._run(_lib.VOTE_V3, masks_d[i], vertex[s:e], hn, 1, thresh, min_num, max_num,
-                                stage=_lib.STAGE_VOTE, workspace=wss[i], **chunk_kw(s, e))["pts"])
-        done = torch.cuda.Event()
-        done.record(cur)
-        st["done"][i] = done
+    if per_image:                             # explicit index tensors were produced on the caller's stream
+        vs.wait_event(ready)
+    with torch.cuda.stream(vs):
+        for i, (s, e) in enumerate(bounds):
+            vs.wait_event(events[i])
+            kps.append(_voting._run(_lib.VOTE_V3, masks_d[i], vertex[s:e], hn, 1, thresh, min_num, max_num,
+                                    stage=_lib.STAGE_VOTE, workspace=wss[i], **chunk_kw(s, e))["pts"])
+            done = torch.cuda.Event()
+            done.record(vs)
+            st["done"][i] = done
+        kpts = torch.cat(kps, 0)
+        voted = torch.cuda.Event()
+        voted.record(vs)
     for m_d in masks_d:
-        m_d.record_stream(cur)
-    # the pose solve is latency-bound (one warp per image): one launch over the whole batch
-    kpts = torch.cat(kps, 0)
+        m_d.record_stream(vs)
+    # the pose solve is latency-bound (one warp per image): one launch over the whole batch, on the caller's stream
+    cur.wait_event(voted)
+    kpts.record_stream(cur)
     out = poses_from_keypoints(kpts, p3d_model, K, bbox_xy=bbox_xy, rate=rate)
     out["kpts"] = kpts
+    fin = torch.cuda.Event()
+    fin.record(cur)
+    pipe.finished[turn] = fin
     if philox:
         if sync_rng:                          # exact: what the reference's loop would have consumed
             cur.wait_stream(gs)

@@ -32,6 +32,17 @@ def step():
     return pipeline.poses_from_vertex(m_h, vh, model, K, round_hyp_num=512, bbox_xy=bbox, rate=rate, sync_rng=False, chunks=chunks)
 for _ in range(3): step()
 torch.cuda.synchronize(); marks.clear()
+def _cg():
+    out = {}
+    for f in ("/sys/fs/cgroup/cpu.stat", "/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.stat", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try: out[f] = open(f).read().strip().replace("\n", "; ")
+        except OSError: pass
+    return out
+print("affinity", len(os.sched_getaffinity(0)), "cpu_count", os.cpu_count(), "torch threads", torch.get_num_threads())
+cg0 = _cg()
+import gc
+if os.environ.get("EPB_GC_FREEZE"):
+    gc.collect(); gc.freeze()
 t0 = torch.cuda.Event(enable_timing=True); t0.record()
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 import time
@@ -42,10 +53,17 @@ for _ in range(nsteps):
 torch.cuda.synchronize()
 if nsteps > 4:
     ends = [t0.elapsed_time(e0) for n, e0, e1 in marks if n == "step_end"]
-    print("gpu step ends:", " ".join("%.2f" % x for x in ends))
-    print("cpu enqueue  :", " ".join("%.2f" % x for x in cpu))
+    cg1 = _cg()
+    for k in cg0: print(k, "\n   before:", cg0[k], "\n   after: ", cg1[k])
+    import numpy as _np
+    gd, cd = _np.diff([0] + ends), _np.diff([0] + cpu)
+    print("gpu step: mean %.2f max %.2f (at %d) | cpu enqueue/step: mean %.2f max %.2f (at %d) | total %.1f ms for %d steps"
+          % (gd.mean(), gd.max(), gd.argmax(), cd.mean(), cd.max(), cd.argmax(), ends[-1], nsteps))
+    if len(sys.argv) > 3:
+        print("gpu step ends:", " ".join("%.2f" % x for x in ends))
+        print("cpu enqueue  :", " ".join("%.2f" % x for x in cpu))
     g = [e0.elapsed_time(e1) for n, e0, e1 in marks if n == "gather"]; v = [e0.elapsed_time(e1) for n, e0, e1 in marks if n == "vote"]
-    print("gather durs:", " ".join("%.2f" % x for x in g)); print("vote durs:", " ".join("%.2f" % x for x in v))
+    print("gather dur mean %.3f max %.3f | vote dur mean %.3f max %.3f" % (_np.mean(g), _np.max(g), _np.mean(v), _np.max(v)))
     sys.exit(0)
 for name, e0, e1 in marks:
     print("%-9s start %7.3f  end %7.3f  dur %6.3f" % (name, t0.elapsed_time(e0), t0.elapsed_time(e1), e0.elapsed_time(e1)))

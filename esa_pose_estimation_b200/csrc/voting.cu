@@ -578,8 +578,11 @@ __host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
   c.fast_ok = 0; c.kf = 0.f; c.gamma = 0.f; c.eh_scale = 0.f; c.eh_abs = 0.f;
   if (!(T >= 0.5 && T < 1.0)) return c;
   const double k = sqrt((1.0 - T) * (1.0 + T)) / T;
-  const double sin_half = sqrt((1.0 - T) * 0.5);
-  const double beta = 10.5 * u / (T * sin_half);
+  // |cos(phi) - T| >= sin(0.75 theta) sin|theta - phi| whenever |theta - phi| <= theta/2 (inside the cone) or
+  // phi > theta; deeper inside the cone the margin is >= 2 sin(theta/2) sin(theta/4), checked here once
+  const double theta = acos(T);
+  if (!(2.0 * sin(0.5 * theta) * sin(0.25 * theta) >= 10.5 * u)) return c;
+  const double beta = 10.5 * u / (T * sin(0.75 * theta));
   const double gamma = beta * (1.0 / k + 1.0) * 1.0001;
   if (!(gamma <= 0.25)) return c;
   // eps_a + eps_p <= (6.2 k + 4.1) u Nm (|h|_1 + |c|_1) with Nm < 2; factor 3 of slack
@@ -593,10 +596,12 @@ __host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
   return c;
 }
 
+constexpr int VOTE_QCAP = 1024;  // deferred undecided pairs per work unit (overflow is resolved in line)
 struct VoteSmem {
   float4 f[2][VOTE_TILE];  // A1 A2 B1 B2
   float2 g[2][VOTE_TILE];  // A3 B3
-  float4 x[2][VOTE_TILE];  // cx cy nx ny as the reference sees them (exact path)
+  unsigned q[VOTE_QCAP];   // undecided (pixel, hypothesis) pairs: t_rel << 11 | thread << 4 | r << 1 | sign(m)
+  unsigned qn;
 };
 
 template <int R>
@@ -684,9 +689,7 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
         const bool valid = q != 0xffffffffu && !((double)n1 < 1e-6) && (s1 <= FLT_MAX);
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         float2 g = make_float2(-INFINITY, 0.f);
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) {
-          x = make_float4(cx, cy, nx, ny);
           if (vc.fast_ok) {
             // exact power-of-two scaling: max(|nx|,|ny|) -> [1,2)
             const float nm = fmaxf(fabsf(nx), fabsf(ny));
@@ -703,7 +706,7 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
           }
         }
         const int slot = k * VOTE_THREADS + threadIdx.x;
-        sm.f[buf][slot] = f; sm.g[buf][slot] = g; sm.x[buf][slot] = x;
+        sm.f[buf][slot] = f; sm.g[buf][slot] = g;
       }
     };
 
@@ -725,19 +728,30 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
       }
       return amb;
     };
-    // rare side path: undecided pairs get the reference expression (IEEE sqrt / div); m becomes +-1
-    auto resolve = [&](const float4 x, float (&m)[R], const float (&w)[R]) {
-      const float n1 = dir_norm(x.z, x.w);
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (!(fabsf(m[r]) > w[r]))
-          m[r] = vote_exact(x.x, x.y, x.z, x.w, n1, half2(HX[r >> 1], r & 1), half2(HY[r >> 1], r & 1), T)
-                     ? 1.0f : -1.0f;
+    // the reference expression (IEEE sqrt / div) for pixel t of this image against hypothesis (hx, hy)
+    auto exact_vote = [&](int t, float hx, float hy) -> bool {
+      if (t >= t_end) return false;                         // padding record
+      const uint32_t q = __ldg(fp + t);
+      const float2 d = __ldg(dir + t);
+      return vote_exact((float)(q & 0xffff), (float)(q >> 16), d.x, d.y, dir_norm(d.x, d.y), hx, hy, T);
+    };
+    // Undecided pairs are rare (~6e-4 of the pairs) and scattered over the lanes: resolving them in line
+    // would run the ~75-instruction reference expression with one or two active lanes.  They are queued
+    // instead (with the sign the fast loop counted) and resolved densely, one pair per lane, after the
+    // tile loop; the owner's count is corrected with an atomic.  A full queue falls back to in-line.
+    unsigned* const qn_ptr = &sm.qn;
+    unsigned* const q_ptr = sm.q;
+    auto defer = [&](int t, int r, float& m, float hx, float hy) {
+      const unsigned pos = atomicAdd(qn_ptr, 1u);
+      if (pos < (unsigned)VOTE_QCAP)
+        q_ptr[pos] = ((unsigned)(t - t_begin) << 11) | (threadIdx.x << 4) | ((unsigned)r << 1) | (__float_as_uint(m) >> 31);
+      else
+        m = exact_vote(t, hx, hy) ? 1.0f : -1.0f;
     };
 
     int buf = 0;
     prefetch(t_begin);
-    __syncthreads();   // previous unit's readers are done with both buffers
+    if (threadIdx.x == 0) sm.qn = 0u;
     stage(0);
     __syncthreads();
     for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE) {
@@ -746,21 +760,27 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
       const int nrec = min(VOTE_TILE, t_end - t0);
       const float4* fr = sm.f[buf];
       const float2* gr = sm.g[buf];
-      const float4* xr = sm.x[buf];
       // RECS records per trip share one branch to the side path; an odd tail record is a padding
       // record of the tile (never an inlier) or, in a full tile, handled by the even tile size
       const int ntrip = (nrec + RECS - 1) / RECS;
+      const float4* frp = fr;
+      const float2* grp = gr;
 #pragma unroll 1
-      for (int it = 0; it < ntrip; ++it) {
+      for (int it = 0; it < ntrip; ++it, frp += RECS, grp += RECS) {
         const int i = it * RECS;
         float m[RECS][R], w[RECS][R];
         bool ambj[RECS], amb = false;
 #pragma unroll
-        for (int j = 0; j < RECS; ++j) { ambj[j] = test_record(fr[i + j], gr[i + j], m[j], w[j]); amb |= ambj[j]; }
+        for (int j = 0; j < RECS; ++j) { ambj[j] = test_record(frp[j], grp[j], m[j], w[j]); amb |= ambj[j]; }
         if (amb) {
 #pragma unroll
           for (int j = 0; j < RECS; ++j)
-            if (ambj[j]) resolve(xr[i + j], m[j], w[j]);
+            if (ambj[j]) {
+#pragma unroll
+              for (int r = 0; r < R; ++r)
+                if (!(fabsf(m[j][r]) > w[j][r]))
+                  defer(t0 + i + j, r, m[j][r], half2(HX[r >> 1], r & 1), half2(HY[r >> 1], r & 1));
+            }
         }
 #pragma unroll
         for (int j = 0; j < RECS; ++j)
@@ -773,6 +793,19 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
     }
 
     int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
+    // deferred pairs: one per lane, reference expression, correction of the count the fast loop produced
+    {
+      const unsigned nq = min(sm.qn, (unsigned)VOTE_QCAP);   // every enqueue precedes the loop's last barrier
+      for (unsigned e = threadIdx.x; e < nq; e += VOTE_THREADS) {
+        const unsigned ent = sm.q[e];
+        const int t = t_begin + (int)(ent >> 11), owner = (ent >> 4) & 127, r = (ent >> 1) & 7;
+        const int h = chunk * VOTE_THREADS * R + (r >> 1) * 2 * VOTE_THREADS + 2 * owner + (r & 1);
+        if (h >= HN) continue;
+        const bool fast_inlier = (ent & 1u) == 0u;
+        const bool exact = exact_vote(t, __ldg(hypx + h), __ldg(hypy + h));
+        if (exact != fast_inlier) atomicAdd(out + h, exact ? 1 : -1);
+      }
+    }
     // records visited by the trips above (tiles are rounded up to a multiple of RECS)
     int visited = 0;
     for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE)

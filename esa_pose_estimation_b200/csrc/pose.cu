@@ -144,9 +144,22 @@ __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
         const double apq = ws.A[p][q];
         double c = 1.0, s = 0.0, t = 0.0;
         if (apq != 0.0) {
-          const double theta = (ws.A[q][q] - ws.A[p][p]) / (2.0 * apq);
-          t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-          c = 1.0 / sqrt(t * t + 1.0);
+          // tan of the rotation angle: t = sgn / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
+          // rewritten without theta as sgn(alpha apq) |apq| / (|alpha| + hypot(alpha, apq)).  Jacobi is
+          // self-correcting in t (an inexact t leaves a residual a_pq that the next sweep removes, the
+          // rotation stays orthogonal as long as c^2 + s^2 = 1), so t is evaluated in float32 with the fast
+          // reciprocal / square root and only c = rsqrt(1 + t^2) in float64: one long FP64 operation on
+          // the critical path of each of the ~80 steps instead of two divisions and two square roots.
+          const double alpha = 0.5 * (ws.A[q][q] - ws.A[p][p]);
+          const double scale = fmax(fabs(alpha), fabs(apq));
+          // exact power-of-two rescale into float32 range (exponent arithmetic, no division)
+          const int e = ((__double2hiint(scale) >> 20) & 0x7ff) - 1023;
+          const double inv = __hiloint2double((1023 - max(min(e, 1022), -1022)) << 20, 0);
+          const float af = (float)(fabs(alpha) * inv), bf = (float)(fabs(apq) * inv);
+          const float tf = __fdividef(bf, af + __fsqrt_rn(af * af + bf * bf));
+          const bool pos = alpha == 0.0 || ((alpha > 0) == (apq > 0));   // sign of theta (theta = +-0 counts as +)
+          t = pos ? (double)tf : -(double)tf;
+          c = rsqrt(t * t + 1.0);
           s = t * c;
         }
         cs[4 * lane] = c; cs[4 * lane + 1] = s; cs[4 * lane + 2] = t; cs[4 * lane + 3] = apq;

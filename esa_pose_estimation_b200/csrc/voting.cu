@@ -321,7 +321,7 @@ __global__ void rng_offsets_kernel(int B, int rounds, unsigned long long base, u
 template <bool PLANAR>
 __global__ void __launch_bounds__(256, 4)
 mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int mask_mode,
-                    Workspace ws, SubsampleCtx sc, const float* __restrict__ vertex, epb_voting_params p) {
+                    Workspace ws, SubsampleCtx sc, const float* __restrict__ vertex, epb_voting_params p, int light) {
   __shared__ int s_warp[8];
   // grid-stride over (image, tile): a full grid for a device-resident field; for a host-resident field
   // the launcher caps the grid at one CTA per SM -- PCIe needs ~100 KB in flight, not the machine, and
@@ -401,25 +401,47 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
     // array (the NCHW network output); quads without foreground are not read at all
     const float* base = vertex + (b / p.classes) * p.sb + seg + lane * 4;
     float2* dst = ws.direct + (size_t)b * p.vn * HW;
-    for (int v = 0; v < p.vn; ++v) {
-      const float* px = base + (long long)v * p.sv;
-      const float* py = px + p.sc;
-      float4 dx[4], dy[4];
+    if (!light) {
+      for (int v = 0; v < p.vn; ++v) {
+        const float* px = base + (long long)v * p.sv;
+        const float* py = px + p.sc;
+        float4 dx[4], dy[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (flags[k]) {
-          dx[k] = ldg_stream_f4(reinterpret_cast<const float4*>(px + k * 128));
-          dy[k] = ldg_stream_f4(reinterpret_cast<const float4*>(py + k * 128));
+        for (int k = 0; k < 4; ++k)
+          if (flags[k]) {
+            dx[k] = ldg_stream_f4(reinterpret_cast<const float4*>(px + k * 128));
+            dy[k] = ldg_stream_f4(reinterpret_cast<const float4*>(py + k * 128));
+          }
+        float2* d = dst + (size_t)v * HW;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float fx[4] = {dx[k].x, dx[k].y, dx[k].z, dx[k].w};
+          const float fy[4] = {dy[k].x, dy[k].y, dy[k].z, dy[k].w};
+          int o = ok[k];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if ((flags[k] >> j) & 1u) d[o++] = make_float2(fx[j], fy[j]);
         }
-      float2* d = dst + (size_t)v * HW;
+      }
+    } else {
+      // host-resident field: two loads in flight per thread are plenty for PCIe and keep the SM's
+      // load/store queues free for the voting kernel that shares the SM
+#pragma unroll 1
+      for (int v = 0; v < p.vn; ++v) {
+        const float* px = base + (long long)v * p.sv;
+        const float* py = px + p.sc;
+        float2* d = dst + (size_t)v * HW;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          if (!flags[k]) continue;
+          const float4 dx = ldg_stream_f4(reinterpret_cast<const float4*>(px + k * 128));
+          const float4 dy = ldg_stream_f4(reinterpret_cast<const float4*>(py + k * 128));
+          const float fx[4] = {dx.x, dx.y, dx.z, dx.w}, fy[4] = {dy.x, dy.y, dy.z, dy.w};
+          int o = ok[k];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float fx[4] = {dx[k].x, dx[k].y, dx[k].z, dx[k].w};
-        const float fy[4] = {dy[k].x, dy[k].y, dy[k].z, dy[k].w};
-        int o = ok[k];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if ((flags[k] >> j) & 1u) d[o++] = make_float2(fx[j], fy[j]);
+          for (int j = 0; j < 4; ++j)
+            if ((flags[k] >> j) & 1u) d[o++] = make_float2(fx[j], fy[j]);
+        }
       }
     }
   }
@@ -1334,12 +1356,15 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     cudaDeviceGetAttribute(&sm_n, cudaDevAttrMultiProcessorCount, dev_id);
     const long long work = (long long)T * p.B;
     static const int per_sm = [] { const char* e = getenv("EPB_GATHER_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
-    const long long cap = (long long)sm_n * (per_sm > 0 ? per_sm : 1);
+    static const int total_cap = [] { const char* e = getenv("EPB_GATHER_CTAS"); return e ? atoi(e) : 0; }();
+    const long long cap = total_cap > 0 ? total_cap : (long long)sm_n * (per_sm > 0 ? per_sm : 1);
     const unsigned g = (unsigned)(host_field && work > cap ? cap : work);
-    mask_scatter_kernel<true><<<g, 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p);
+    static const int light_knob = [] { const char* e = getenv("EPB_GATHER_LIGHT"); return e ? atoi(e) : 1; }();
+    mask_scatter_kernel<true><<<g, 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p,
+                                                host_field && light_knob);
     EPB_RETURN_IF(check_launch());
   } else {
-    mask_scatter_kernel<false><<<(unsigned)((long long)T * p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p);
+    mask_scatter_kernel<false><<<(unsigned)((long long)T * p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p, 0);
     EPB_RETURN_IF(check_launch());
     field_gather_kernel<<<dim3((HW + 255) / 256, p.B), 256, 0, s>>>(io->vertex, p, ws);
     EPB_RETURN_IF(check_launch());

@@ -65,14 +65,16 @@ def poses_from_vertex(mask, vertex, p3d_model, K, round_hyp_num=512, inlier_thre
 
 
 class _HostPipe:
-    """Per (device, stream) state of the host-input pipeline: the high-priority gather stream and a
-    ring of two workspace sets, so that the gather of call n+1 may start while call n still votes."""
+    """Per (device, stream) state of the host-input pipeline: the high-priority gather stream, the voting
+    stream and a ring of DEPTH workspace sets, so that the gather of call n+1 (and the host-side enqueue of
+    call n+2) proceed while call n still votes."""
+    DEPTH = 2
 
     def __init__(self, dev):
         self.gs = torch.cuda.Stream(device=dev, priority=-1)
         self.vs = torch.cuda.Stream(device=dev)              # voting; the caller's stream only solves the poses
-        self.sets = [None, None]          # each: dict(ws=[tensors], done=[events], need=int)
-        self.finished = [None, None]      # event after the pose solve of the call that last used the set
+        self.sets = [None] * self.DEPTH       # each: dict(ws=[tensors], done=[events], need=int)
+        self.finished = [None] * self.DEPTH   # event after the pose solve of the call that last used the set
         self.turn = 0
 
 
@@ -107,8 +109,8 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
     per = max(e - s for s, e in bounds)
     need = _voting.workspace_bytes(per, h, w, vn, hn)
     turn = pipe.turn
-    # At most two calls in flight: the host waits (spinning on an event) for the call that used this
-    # workspace set two turns ago.  Without it a host that enqueues faster than the GPU drains fills the
+    # At most DEPTH calls in flight: the host waits (spinning on an event) for the call that used this
+    # workspace set DEPTH turns ago.  Without it a host that enqueues faster than the GPU drains fills the
     # gather stream's launch queue, and the driver then parks the enqueueing thread for up to ~100 ms
     # (measured: tools/stallhunt.py), long enough to starve the GPU.
     if pipe.finished[turn] is not None:
@@ -118,7 +120,7 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
         st = pipe.sets[turn] = dict(
             ws=[torch.empty((need,), dtype=torch.uint8, device=dev) for _ in range(chunks)],
             done=[None] * chunks, need=need)
-    pipe.turn ^= 1
+    pipe.turn = (turn + 1) % pipe.DEPTH
     wss = st["ws"]
     kw = dict(kw)
     sync_rng = kw.pop("sync_rng", True)
@@ -147,7 +149,7 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
     with torch.cuda.stream(gs):
         for i, (s, e) in enumerate(bounds):
             if st["done"][i] is not None:
-                gs.wait_event(st["done"][i])          # the call two turns ago has consumed this workspace
+                gs.wait_event(st["done"][i])          # the call DEPTH turns ago has consumed this workspace
             m = mask[s:e]
             m_d = m if m.is_cuda else m.to(dev, non_blocking=True)
             _voting._run(_lib.VOTE_V3, m_d, vertex[s:e], hn, 1, thresh, min_num, max_num,

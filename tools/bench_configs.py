@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Secondary configurations of BASELINE.json (bench.py measures configs[1], the contract line):
+
+  C1  single SPEED frame, 11-keypoint 128x128 heatmaps: decode + EPnP-RANSAC + LM   (latency)
+  C3  heatmap path at 384x384, the per-GPU share of the 3000-frame validation set     (poses/s, decode GB/s)
+  C4  768x768 vector fields, 2048 hypotheses/keypoint, voting distribution + uncertainty PnP
+  C5  batched LM refinement sweep, 1e3..1e6 poses x 11 points
+
+One JSON line per configuration (same conventions as bench.py: CUDA events on the launching
+stream, >= 3 warm-ups, inputs resident in HBM and larger than L2 or rotated, no host sync inside).
+    python tools/bench_configs.py [c1 c3 c4 c5]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from esa_pose_estimation_b200 import _lib, inference, pipeline, pnp as gp, ransac_voting_gpu as rv  # noqa: E402
+from tests.synth import ESA_K, make_pose_case, make_vertex_field, tango_model  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+PEAK = 6552.3
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def prof(cls):
+    tot, n = _lib.c_double(0), _lib.c_int(0)
+    _lib.load().epb_profile_read(cls, tot, n)
+    return tot.value, n.value
+
+
+def heatmap_batch(n, kp, s, seed):
+    """Heatmaps of n frames whose peaks are the projections of the model under random poses (device-side)."""
+    model = tango_model(kp, seed=9)
+    crop = np.zeros((n, kp, 2), np.float32); bbox = np.zeros((n, 2)); rate = np.zeros(n)
+    for i in range(n):
+        c = make_pose_case(seed * 7919 + i, kp, 0.0, 0, model=model)
+        lo, hi = c["p2d"].min(0), c["p2d"].max(0)
+        size = (hi - lo).max() * 1.3 + 8
+        bbox[i] = (lo + hi) / 2 - size / 2
+        rate[i] = s / size
+        crop[i] = (c["p2d"] - bbox[i]) * rate[i]
+    ys = torch.arange(s, device=DEV, dtype=torch.float32).view(1, 1, s, 1)
+    xs = torch.arange(s, device=DEV, dtype=torch.float32).view(1, 1, 1, s)
+    c_t = torch.from_numpy(crop).to(DEV)
+    g = torch.Generator(device=DEV); g.manual_seed(seed)
+    hm = torch.empty((n, kp, s, s), device=DEV)
+    for i0 in range(0, n, 25):
+        cc = c_t[i0:i0 + 25]
+        d2 = (xs - cc[:, :, 0, None, None]) ** 2 + (ys - cc[:, :, 1, None, None]) ** 2
+        hm[i0:i0 + 25] = torch.exp(-d2 / 8.0) * 0.9 + 0.01 * torch.randn(d2.shape, device=DEV, generator=g)
+    return hm, torch.from_numpy(bbox).to(DEV), torch.from_numpy(rate).to(DEV), torch.from_numpy(model).to(DEV)
+
+
+def c1():
+    hm, bbox, rate, model = heatmap_batch(8, 11, 128, 1)
+    K = torch.from_numpy(ESA_K).to(DEV)
+    i = [0]
+
+    def step():
+        k = i[0] % 8; i[0] += 1
+        return pipeline.poses_from_heatmaps(hm[k:k + 1], bbox[k:k + 1], rate[k:k + 1], model, K, min_k=8)
+    ms = timed(step, 50)
+    return {"config": "C1 single frame 11x128x128 heatmaps -> decode + EPnP-RANSAC + LM (device resident, no sync inside)",
+            "metric": "latency per frame", "value": ms * 1e3, "unit": "us", "higher_is_better": False,
+            "note": "reference val.py path on the CPU: ~0.8 ms decode + 0.5 ms cv2 EPnP + LM per frame (SURVEY 8d)"}
+
+
+def c3():
+    n, kp, s = 125, 11, 384                      # 0.81 GB of heatmaps per call (3 calls = the 375-frame GPU share)
+    hm, bbox, rate, model = heatmap_batch(n, kp, s, 2)
+    K = torch.from_numpy(ESA_K).to(DEV)
+    lib = _lib.load()
+    lib.epb_profile_enable(1)
+    steps = 10
+    ms = timed(lambda: pipeline.poses_from_heatmaps(hm, bbox, rate, model, K, min_k=8), steps)
+    dec_ms, dec_n = prof(5)
+    pose_ms, pose_n = prof(4)
+    lib.epb_profile_enable(0)
+    per = dec_ms / dec_n
+    bytes_ = hm.numel() * 4 + n * kp * 16
+    return {"config": "C3 heatmap path, 125 frames x 11 x 384x384 per call (per-GPU share of the 3000-frame set = 3 calls)",
+            "metric": "poses/sec (heatmaps -> refined pose)", "value": n / (ms * 1e-3), "unit": "poses/s",
+            "ms_per_call": ms, "kernel_ms": {"decode": per, "pose": pose_ms / pose_n},
+            "roofline": {"kernel": "decode_kernel", "bound": "hbm", "achieved": bytes_ / (per * 1e-3) / 1e9, "peak": PEAK,
+                         "unit": "GB/s", "frac": bytes_ / (per * 1e-3) / 1e9 / PEAK, "algorithmic_bytes_per_launch": bytes_,
+                         "l2_policy": "input (0.81 GB) larger than L2"}}
+
+
+def c4():
+    b, s, vn, hn, rounds = 8, 768, 11, 256, 8
+    mask, vertex, _ = make_vertex_field(3, 2, s, s, vn, 0.25, noise_deg=2.0)
+    mask = np.tile(mask, (b // 2, 1, 1)); vertex = np.tile(vertex, (b // 2, 1, 1, 1))
+    m_t = torch.from_numpy(mask).to(DEV)
+    v_t = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(DEV))
+    lib = _lib.load()
+    lib.epb_profile_enable(1)
+    torch.manual_seed(3)
+    ms = timed(lambda: rv.estimate_voting_distribution(m_t, v_t, round_hyp_num=hn, min_hyp_num=hn * rounds, topk=128,
+                                                       sync_rng=False), 5)
+    vote_ms, vote_n = prof(2)
+    lib.epb_profile_enable(0)
+    tn = float(np.minimum(mask.reshape(b, -1).sum(1), 30000).mean())
+    tests = b * hn * rounds * vn * tn
+    return {"config": "C4 8 x 768x768 fields, 11 keypoints, 8 rounds x 256 = 2048 hypotheses, voting mean/covariance "
+                      "(foreground 0.25 -> max_num subsample to ~30000 px)",
+            "metric": "images/sec (vector field -> voting distribution)", "value": b / (ms * 1e-3), "unit": "images/s",
+            "ms_per_call": ms, "kernel_ms": {"vote_count": vote_ms / vote_n},
+            "roofline": {"kernel": "vote_count_kernel", "bound": "fp32-issue", "pair_tests_per_s": tests / (vote_ms / vote_n * 1e-3),
+                         "alu_frac": 6 * tests / (vote_ms / vote_n * 1e-3) / (148 * 128 * 1.965e9)}}
+
+
+def c5():
+    out = []
+    model = tango_model(11, seed=9)
+    K = torch.from_numpy(ESA_K).to(DEV)
+    rng = np.random.default_rng(5)
+    base = 1000
+    p2d = np.zeros((base, 11, 2)); init = np.zeros((base, 6))
+    for i in range(base):
+        c = make_pose_case(9000 + i, 11, 0.5, 0, model=model)
+        p2d[i] = c["p2d"]
+        init[i, :3] = c["rvec"] + rng.normal(0, np.deg2rad(2.0) / np.sqrt(3), 3)      # ~2 deg off
+        init[i, 3:] = c["t"] * (1 + rng.normal(0, 0.02, 3))                             # 2 % off
+    for n in (1000, 10000, 100000, 1000000):
+        reps = n // base
+        p2 = torch.from_numpy(np.tile(p2d, (reps, 1, 1))).to(DEV)
+        it = torch.from_numpy(np.tile(init, (reps, 1))).to(DEV)
+        w = torch.ones((n, 11, 3), dtype=torch.float64, device=DEV); w[:, :, 1] = 0
+        m = torch.from_numpy(model).to(DEV)
+        ms = timed(lambda: gp.lm_refine_batch(p2, m, w, K, it), 5 if n >= 100000 else 20)
+        _, iters, _ = gp.lm_refine_batch(p2, m, w, K, it, return_info=True)
+        out.append({"poses": n, "ms": ms, "poses_per_s": n / (ms * 1e-3), "mean_lm_iterations": float(iters.float().mean())})
+    return {"config": "C5 batched LM refinement sweep, 11-point model, start 2 deg / 2 % off", "metric": "poses/sec (LM only)",
+            "unit": "poses/s", "value": out[-1]["poses_per_s"], "sweep": out,
+            "note": "reference analogue (uncertainty_pnp.cpp over TinySolver, 1 core): ~3.8e4 poses/s (SURVEY 8d)"}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c3", "c4", "c5"]
+    for name in which:
+        r = {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[name]()
+        r["gpu"] = torch.cuda.get_device_name(0)
+        print(json.dumps(r))
+        sys.stdout.flush()

@@ -28,6 +28,10 @@ def wrapped(*args, **kw):
     marks.append((("all", "gather", "vote")[st], e0, e1))
     return r
 rv._run = wrapped
+if os.environ.get("EPB_NO_POSE"):
+    def _nopose(kpts, *a, **k):
+        return {"pose7": kpts.new_zeros((kpts.shape[0], 7))}
+    pipeline.poses_from_keypoints = _nopose
 def step():
     return pipeline.poses_from_vertex(m_h, vh, model, K, round_hyp_num=512, bbox_xy=bbox, rate=rate, sync_rng=False, chunks=chunks)
 for _ in range(3): step()

@@ -512,15 +512,31 @@ __device__ int ransac_update_num_iters(double p, double ep, int model_points, in
 // cv2.solvePnPRansac(flags=EPNP) restated (oracle/epnp_port.py solve_pnp_ransac_epnp).
 // pw/u/v are this lane's correspondence (already rounded to float32 by the caller, as
 // OpenCV converts its inputs to CV_32F).  Returns status; all lanes hold the same result.
+//
+// Two warps per image (CTA = 64 threads).  OpenCV ends with one EPnP over the consensus set; on clean
+// frames that set is "all points" and is known only after the first 5-point sample has been solved and
+// scored.  Warp 1 (role 1) therefore solves EPnP over ALL points speculatively while warp 0 (role 0)
+// runs the RANSAC loop; when the consensus turns out to be everything -- the common case -- warp 0 takes
+// warp 1's result instead of starting the second eigen-solve, which removes ~40 % of the latency of this
+// latency-bound kernel.  Otherwise nothing changes (the speculative result is dropped).  Exactly one
+// __syncthreads() is executed on every path of both roles.
 __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw[3], double u, double v,
                                const Cam& cam, double reproj_err, int max_iters, double confidence,
-                               PoseRT& out, unsigned& inlier_mask) {
+                               PoseRT& out, unsigned& inlier_mask, int role, PoseRT* s_spec) {
   const int model_points = 5;
   inlier_mask = 0;
   if (n < model_points) return EPB_POSE_TOO_FEW;
   const unsigned all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+  if (role == 1) {
+    PoseRT sp;
+    epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
+    if (lane == 0) *s_spec = sp;
+    __syncthreads();
+    return EPB_POSE_OK;
+  }
   if (n == model_points) {
-    epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, out);
+    __syncthreads();
+    out = *s_spec;
     inlier_mask = all;
     return EPB_POSE_OK;
   }
@@ -528,6 +544,7 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   int niters = max_iters;
   unsigned best_mask = 0;
   int best_count = 0;
+  bool synced = false;
   const float thr2 = (float)(reproj_err * reproj_err);
   for (int it = 0; it < niters; ++it) {
     int idx[5];
@@ -558,9 +575,12 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
         niters = ransac_update_num_iters(confidence, (double)(n - cnt) / n, model_points, niters);
       }
     }
+    if (!synced) { __syncthreads(); synced = true; }
   }
+  if (!synced) __syncthreads();
   if (best_mask == 0) return EPB_POSE_FAILED;
-  epnp_core(ws, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
+  if (best_mask == all) out = *s_spec;   // == epnp_core over all points, first_lane 0
+  else epnp_core(ws, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
   inlier_mask = best_mask;
   return EPB_POSE_OK;
 }
@@ -808,14 +828,15 @@ __device__ __forceinline__ Cam load_cam(const double* K, int batched, int img) {
 }
 __device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
 
-__global__ void __launch_bounds__(POSE_WARPS * 32)
+__global__ void __launch_bounds__(64)
 pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __restrict__ p2d,
            const double* __restrict__ K, int K_batched, const int32_t* __restrict__ npts, int B,
            int n_max, double reproj_err, int max_iters, double confidence, double* __restrict__ rt34,
            unsigned long long* __restrict__ inlier_mask, int32_t* __restrict__ status) {
-  __shared__ WarpScratch scratch[POSE_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x * (blockDim.x >> 5) + warp;
+  __shared__ WarpScratch scratch[2];
+  __shared__ PoseRT s_spec;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp = role (0 RANSAC, 1 speculative)
+  const int img = blockIdx.x;
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
   const int n = npts ? min(npts[img], n_max) : n_max;
@@ -830,8 +851,9 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
   const Cam cam = load_cam(K, K_batched, img);
   PoseRT out;
   unsigned mask = 0;
-  const int st = pnp_ransac_epnp(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask);
-  if (lane == 0) {
+  const int st = pnp_ransac_epnp(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
+                                 &s_spec);
+  if (warp == 0 && lane == 0) {
     double* o = rt34 + (size_t)img * 12;
     if (st == EPB_POSE_OK) {
 #pragma unroll
@@ -927,17 +949,18 @@ __global__ void cov_to_weights_kernel(const float* __restrict__ cov, int n, doub
 }
 
 // val.py:172-228 for a batch: one warp per frame, lane k <-> keypoint k (K <= 32)
-__global__ void __launch_bounds__(POSE_WARPS * 32)
+__global__ void __launch_bounds__(64)
 pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ maxvals,
                      const double* __restrict__ bbox_xy, const double* __restrict__ rate,
                      const double* __restrict__ p3d_model, const double* __restrict__ Kmat, int B, int K,
                      int min_k, double sel_thresh, int weighted, float* __restrict__ pose7,
                      double* __restrict__ rt6_out, double* __restrict__ epnp_rt34,
                      int32_t* __restrict__ status) {
-  __shared__ WarpScratch scratch[POSE_WARPS];
-  __shared__ double s_pts[POSE_WARPS][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int img = blockIdx.x * (blockDim.x >> 5) + warp;
+  __shared__ WarpScratch scratch[2];
+  __shared__ PoseRT s_spec;
+  __shared__ double s_pts[2][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order (one copy per role)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp = role (0 RANSAC + LM, 1 speculative EPnP)
+  const int img = blockIdx.x;
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
   // --- keypoint selection (val.py:172-177): large_k = max(#(maxval > 0.8), 24), top large_k by maxval
@@ -972,7 +995,9 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   const double pwf[3] = {round_f32(pt[0]), round_f32(pt[1]), round_f32(pt[2])};
   PoseRT init;
   unsigned mask = 0;
-  const int st = pnp_ransac_epnp(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask);
+  const int st = pnp_ransac_epnp(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask, warp,
+                                 &s_spec);
+  if (warp == 1) return;
   double x[6];
   if (st == EPB_POSE_OK) {
     matrix_to_rodrigues(init.R, x);
@@ -1038,7 +1063,7 @@ extern "C" int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const dou
                                    unsigned long long* inlier_mask, int32_t* status, void* stream) {
   if (!p3d || !p2d || !K || !rt34 || B < 0 || n_max <= 0 || n_max > 32 || max_iters < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
-  int grid, block; pose_launch_shape(B, &grid, &block);
+  const int grid = B, block = 64;   // two warps per image: RANSAC + speculative all-point EPnP
   pnp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       p3d, p3d_batched, p2d, K, K_batched, npts, B, n_max, reproj_err, max_iters, confidence, rt34,
       inlier_mask, status);
@@ -1088,7 +1113,7 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
   if (!pose7 && !rt6) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   ProfScope ps(PROF_POSE, (cudaStream_t)stream);
-  int grid, block; pose_launch_shape(B, &grid, &block);
+  const int grid = B, block = 64;
   pose_pipeline_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
       preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6,
       epnp_rt34, status);

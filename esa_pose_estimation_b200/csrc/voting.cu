@@ -384,6 +384,10 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
     }
   }
   uint32_t* out = ws.fgpix + (size_t)b * HW;
+  // gridDim.y CTAs share one tile: each gathers a slice of the keypoints, the first also writes fgpix
+  const int v_per = (p.vn + gridDim.y - 1) / gridDim.y;
+  const int v_lo = blockIdx.y * v_per, v_hi = min(p.vn, v_lo + v_per);
+  if (blockIdx.y == 0)
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int q0 = seg + k * 128 + lane * 4;
@@ -402,7 +406,7 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
     const float* base = vertex + (b / p.classes) * p.sb + seg + lane * 4;
     float2* dst = ws.direct + (size_t)b * p.vn * HW;
     if (!light) {
-      for (int v = 0; v < p.vn; ++v) {
+      for (int v = v_lo; v < v_hi; ++v) {
         const float* px = base + (long long)v * p.sv;
         const float* py = px + p.sc;
         float4 dx[4], dy[4];
@@ -427,7 +431,7 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
       // host-resident field: two loads in flight per thread are plenty for PCIe and keep the SM's
       // load/store queues free for the voting kernel that shares the SM
 #pragma unroll 1
-      for (int v = 0; v < p.vn; ++v) {
+      for (int v = v_lo; v < v_hi; ++v) {
         const float* px = base + (long long)v * p.sv;
         const float* py = px + p.sc;
         float2* d = dst + (size_t)v * HW;
@@ -1360,8 +1364,16 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     const long long cap = total_cap > 0 ? total_cap : (long long)sm_n * (per_sm > 0 ? per_sm : 1);
     const unsigned g = (unsigned)(host_field && work > cap ? cap : work);
     static const int light_knob = [] { const char* e = getenv("EPB_GATHER_LIGHT"); return e ? atoi(e) : 1; }();
-    mask_scatter_kernel<true><<<g, 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p,
-                                                host_field && light_knob);
+    // device-resident field: split the keypoints over gridDim.y so that the grid is several waves deep
+    // (the gather is HBM-bound and each CTA is register-heavy); host field: one slim persistent wave
+    static const int vsplit_knob = [] { const char* e = getenv("EPB_GATHER_VSPLIT"); return e ? atoi(e) : 0; }();
+    int vsplit = 1;
+    if (!host_field) {
+      vsplit = vsplit_knob > 0 ? vsplit_knob : (work < 16LL * sm_n ? 2 : 1);
+      if (vsplit > p.vn) vsplit = p.vn;
+    }
+    mask_scatter_kernel<true><<<dim3(g, vsplit), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p,
+                                                              host_field && light_knob);
     EPB_RETURN_IF(check_launch());
   } else {
     mask_scatter_kernel<false><<<(unsigned)((long long)T * p.B), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p, 0);

@@ -153,6 +153,27 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- our arm
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs next to its GPU BEFORE the pinned host buffers are allocated (first
+    touch places them on that NUMA node): the zero-copy gather of the e2e path then reads host memory
+    that is local to the GPU's PCIe root instead of crossing the socket interconnect.  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus of %s" % (len(cpus), path.split("/")[-2])
+    except Exception as e:                      # no sysfs / no permission: keep the default placement
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 class ClockSampler:
     """One `nvidia-smi -lms` process for the whole run, started BEFORE the warm-up (its start-up takes
     driver locks for a few hundred ms and must not fall into a timed region); samples carry wall-clock
@@ -240,6 +261,7 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    numa = bind_to_gpu_numa_node(local) if not os.environ.get("EPB_NO_NUMA_BIND") else "disabled"
 
     # --- data: 8 distinct structured crops per rank, tiled to the batch (content repeats, the
     # working set per step -- 369 MB of field at the default size -- is larger than the 126 MB L2)
@@ -367,7 +389,7 @@ def run_ours(a):
                    "l2_policy": "inputs larger than L2 (%.0f MB of vector field per step)" % (vertex_h.numel() * 4 / 1e6),
                    "parallelism": "images sharded by batch, 1 NCCL all_gather of poses" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes, "clocks": clocks_e2e,
+                "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes, "clocks": clocks_e2e, "host_numa_binding": numa,
                 "transfer": "mask cudaMemcpyAsync from pinned memory; field read zero-copy from pinned memory by "
                             "field_gather_kernel (foreground pixels only); poses D2H into pinned memory"},
         "gpu_launches": int(launches),

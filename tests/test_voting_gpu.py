@@ -374,3 +374,27 @@ def test_vanishing_point_primitives_bit_exact_vs_reference_kernels(cuda_dev, kin
         inl_c = np.zeros((hn, vn, tn), np.uint8)
         ov.voting_for_hypothesis_vanishing_point(direct, coords, hyp_ref.cpu().numpy(), inl_c, thresh)
         np.testing.assert_array_equal(inl_c, inl_ref.cpu().numpy())
+
+
+@pytest.mark.parametrize("hn,rounds", [(1024, 1), (384, 3), (130, 1)])
+def test_counts_bit_exact_for_large_hypothesis_sets(cuda_dev, hn, rounds):
+    """More than 512 hypotheses per keypoint switch vote_count to 8 hypotheses per thread and several
+    chunks; odd sizes exercise the partial last pair.  Counts against the C restatement, bit-exact."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    b, h, w, vn = 2, 56, 64, 3
+    mask, vertex, _ = make_vertex_field(91 + hn, b, h, w, vn, 0.5, noise_deg=1.5)
+    mask = (mask != 0).astype(np.uint8)
+    vx = vertex_hwvn2(vertex)
+    idxs, _, fn, sel = _idxs_for(mask, vx, hn, rounds, 30000, 23, eq1=True)
+    dbg = rv.voting_debug(_lib.VOTE_DISTRIBUTION, torch.from_numpy(mask).to(cuda_dev),
+                          rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev)), hn, rounds=rounds,
+                          inlier_thresh=0.99, topk=64, idxs=torch.from_numpy(idxs).to(cuda_dev))
+    cnt = dbg["counts"].cpu().numpy()
+    hyp = dbg["hyp"].cpu().numpy()
+    for bi in range(b):
+        _, coords, direct = ov.compact(mask[bi] == 1, vx[bi], 30000, sel, bi)
+        for r in range(rounds):
+            sl = slice(r * hn, (r + 1) * hn)
+            hyp_o = ov.generate_hypothesis(direct, coords, idxs[bi, r])
+            np.testing.assert_array_equal(hyp[bi, sl].view(np.int32), hyp_o.view(np.int32))
+            np.testing.assert_array_equal(cnt[bi, sl], ov.vote_counts(direct, coords, hyp_o, 0.99))

@@ -394,7 +394,12 @@ def run_ours(a):
                             "field_gather_kernel (foreground pixels only); poses D2H into pinned memory"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "vote_count_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the
+                     # ncu --set full capture summarised in profiles/r1_vote_count_full.md (100.9 MB + 5.4 MB): well
+                     # BELOW the algorithmic bytes, because only the foreground of the field is ever touched
+                     "traffic": 106282752 if (a.batch, a.size, a.vn, a.hn, a.fg) == (64, 256, 11, 512, 0.25) else None,
+                     "traffic_source": "profiles/r1_vote_count_full.md", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_s * 1e3,
                      "share_of_step": (vote_ms / a.steps) / step_ms if step_ms > 0 else None,
                      "note": "FP32-ALU-bound at this foreground (SURVEY 8d): see alu",

@@ -288,11 +288,13 @@ def test_counts_exact_on_the_cone_boundary(cuda_dev, thresh):
     assert cnt_o.max() > 100 and cnt_o.min() < cnt_o.max()               # the case is not vacuous
 
 
-def test_pinned_host_field_is_read_in_place(cuda_dev):
+@pytest.mark.parametrize("h,w", [(72, 88), (33, 47)])
+def test_pinned_host_field_is_read_in_place(cuda_dev, h, w):
     """A float32 field in pinned HOST memory (zero-copy gather over PCIe) gives bit-identical results
-    to the device-resident field; pageable host memory is rejected like the reference's CHECK_CUDA."""
+    to the device-resident field; pageable host memory is rejected like the reference's CHECK_CUDA.
+    72x88 takes the planar whole-line gather, 33x47 (H*W not a multiple of 16) the generic strided one."""
     from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
-    b, h, w, vn, hn = 3, 72, 88, 5, 128
+    b, vn, hn = 3, 5, 128
     mask, vertex, _ = make_vertex_field(61, b, h, w, vn, 0.4)
     mask[1, :, : w // 3] = 0
     idxs, _, _, _ = _idxs_for(mask, vertex_hwvn2(vertex), hn, 1, 30000, 3)

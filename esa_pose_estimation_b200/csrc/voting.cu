@@ -976,16 +976,27 @@ winner_refine_kernel(epb_voting_params p, Workspace ws,
   for (int pass = 0; pass < passes; ++pass) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) acc[i] = 0;
-    for (int t = threadIdx.x; t < tn; t += 256) {
-      const uint32_t q = __ldg(fp + t);
-      const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
-      const float2 d = __ldg(dir + t);
-      const float dx = d.x, dy = d.y;
-      if (vote_exact(cx, cy, dx, dy, dir_norm(dx, dy), win.x, win.y, p.inlier_thresh)) {
-        const double nx = dy, ny = -(double)dx;  // normal = (d_y, -d_x), :580-581
-        const double bb = nx * cx + ny * cy;
-        acc[0] += nx * nx; acc[1] += nx * ny; acc[2] += ny * ny;
-        acc[3] += nx * bb; acc[4] += ny * bb; acc[5] += bb * bb; acc[6] += 1.0;
+    // four pixels per trip with their loads issued up front: the loop is bound by the latency of the
+    // (L2-resident) fgpix / direct loads, not by arithmetic
+    for (int t0 = threadIdx.x; t0 < tn; t0 += 4 * 256) {
+      uint32_t q4[4]; float2 d4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + j * 256;
+        q4[j] = t < tn ? __ldg(fp + t) : 0u;
+        d4[j] = t < tn ? __ldg(dir + t) : make_float2(0.f, 0.f);   // zero direction: never an inlier
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t q = q4[j];
+        const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
+        const float dx = d4[j].x, dy = d4[j].y;
+        if (vote_exact(cx, cy, dx, dy, dir_norm(dx, dy), win.x, win.y, p.inlier_thresh)) {
+          const double nx = dy, ny = -(double)dx;  // normal = (d_y, -d_x), :580-581
+          const double bb = nx * cx + ny * cy;
+          acc[0] += nx * nx; acc[1] += nx * ny; acc[2] += ny * ny;
+          acc[3] += nx * bb; acc[4] += ny * bb; acc[5] += bb * bb; acc[6] += 1.0;
+        }
       }
     }
     block_sum_d<7>(acc, s_red);
@@ -1023,11 +1034,18 @@ winner_refine_kernel(epb_voting_params p, Workspace ws,
   if (p.mode == EPB_VOTE_V5 && aux) {
     // confidence = share of pixels voting for the refined point at the literal 0.999 (:848-850)
     int c = 0;
-    for (int t = threadIdx.x; t < tn; t += 256) {
-      const uint32_t q = __ldg(fp + t);
-      const float2 d = __ldg(dir + t);
-      const float dx = d.x, dy = d.y;
-      c += vote_exact((float)(q & 0xffff), (float)(q >> 16), dx, dy, dir_norm(dx, dy), fxp, fyp, 0.999f);
+    for (int t0 = threadIdx.x; t0 < tn; t0 += 4 * 256) {
+      uint32_t q4[4]; float2 d4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + j * 256;
+        q4[j] = t < tn ? __ldg(fp + t) : 0u;
+        d4[j] = t < tn ? __ldg(dir + t) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        c += vote_exact((float)(q4[j] & 0xffff), (float)(q4[j] >> 16), d4[j].x, d4[j].y, dir_norm(d4[j].x, d4[j].y),
+                        fxp, fyp, 0.999f);
     }
     double cc[1] = {(double)c};
     block_sum_d<1>(cc, s_red);

@@ -312,14 +312,15 @@ __global__ void rng_offsets_kernel(int B, int rounds, unsigned long long base, u
 // ------------------------------------------------------------------------------------------
 // 4. mask_scatter: stable compaction of foreground pixel coordinates.
 // ------------------------------------------------------------------------------------------
-// Pixel ownership inside a tile of 4096: warp w owns the 512 pixels [512 w, 512 w + 512); lane l owns
-// the four quads {128 k + 4 l .. + 3}, k = 0..3.  Every warp-level access (mask bytes, field float4s)
-// is then one contiguous run -- 128 B of mask, 512 B of a field plane -- i.e. whole, aligned 128-byte
-// lines, the only access shape that keeps in-place PCIe reads of a host-resident field at full-size
-// requests (tools/micro/zerocopy_bw.cu: 51 GB/s contiguous vs 12-30 GB/s with sector-sized pieces).
-// Output order is still the row-major rank of the pixel (what torch.nonzero gives).
+// Pixel ownership inside a tile of 4096: warp w owns the 512 pixels [512 w, 512 w + 512) as 16 groups of
+// 32 consecutive pixels, lane l owns pixel 32 g + l of every group g.  Every warp-level access is then
+// one contiguous run: 32 mask bytes, one aligned 128-byte line of a field plane, and -- after the
+// ballot-based compaction -- one contiguous run of the output.  Whole lines are the only access shape that
+// keeps in-place PCIe reads of a host-resident field at full-size requests (tools/micro/zerocopy_bw.cu:
+// 51 GB/s contiguous vs 12-30 GB/s with sector-sized pieces), and contiguous float2 stores keep the L2 write
+// path at one transaction per sector.  Output order is the row-major rank of the pixel (torch.nonzero).
 template <bool PLANAR>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int mask_mode,
                     Workspace ws, SubsampleCtx sc, const float* __restrict__ vertex, epb_voting_params p, int light) {
   __shared__ int s_warp[8];
@@ -338,113 +339,67 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
   const bool sub = ws.sub[b] != 0;
   const float ratio = ws.ratio[b];
   const unsigned long long off_u = ws.off_u[b];
-  unsigned flags[4];
-  unsigned packed = 0;   // foreground count of quad k in byte k
+  unsigned mine = 0;      // bit g: this lane's pixel of group g is foreground
+  int pos[16];               // rank of the lane's pixel of group g inside the warp's segment
+  int wtotal = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int q0 = seg + k * 128 + lane * 4;
-    unsigned char bytes[4] = {0, 0, 0, 0};
-    if (q0 + 4 <= HW && ((reinterpret_cast<uintptr_t>(m + q0) & 3) == 0)) {
-      *reinterpret_cast<unsigned*>(bytes) = __ldg(reinterpret_cast<const unsigned*>(m + q0));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bytes[j] = (q0 + j < HW) ? m[q0 + j] : 0;
+  for (int g = 0; g < 16; ++g) {
+    const int px = seg + g * 32 + lane;
+    bool f = false;
+    if (px < HW) {
+      f = mask_pred(__ldg(m + px), mask_mode, cls);
+      if (f && sub) f = keep_pixel(sc, b, HW, px, ratio, off_u);
     }
-    unsigned f4 = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bool f = (q0 + j < HW) && mask_pred(bytes[j], mask_mode, cls);
-      if (f && sub) f = keep_pixel(sc, b, HW, q0 + j, ratio, off_u);
-      f4 |= (unsigned)f << j;
-    }
-    flags[k] = f4;
-    packed |= (unsigned)__popc(f4) << (8 * k);
+    const unsigned bal = __ballot_sync(FULL, f);
+    mine |= (unsigned)f << g;
+    pos[g] = wtotal + __popc(bal & ((1u << lane) - 1u));
+    wtotal += __popc(bal);
   }
-  // byte-wise inclusive scan over the lanes (a quad-group holds at most 128 pixels: no carry between bytes)
-  unsigned incl = packed;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const unsigned o = __shfl_up_sync(FULL, incl, d);
-    if (lane >= d) incl += o;
-  }
-  const unsigned tot = __shfl_sync(FULL, incl, 31);
-  const unsigned excl = incl - packed;
-  const int wtotal = (int)((tot & 255u) + ((tot >> 8) & 255u) + ((tot >> 16) & 255u) + (tot >> 24));
   if (lane == 0) s_warp[warp] = wtotal;
   __syncthreads();
   int wbase = ws.tile_offsets[(size_t)b * T + tile];
   for (int w = 0; w < warp; ++w) wbase += s_warp[w];
-  int ok[4];   // rank of the first foreground pixel of quad k
-  {
-    int kb = wbase;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      ok[k] = kb + (int)((excl >> (8 * k)) & 255u);
-      kb += (int)((tot >> (8 * k)) & 255u);
-    }
-  }
-  uint32_t* out = ws.fgpix + (size_t)b * HW;
   // gridDim.y CTAs share one tile: each gathers a slice of the keypoints, the first also writes fgpix
   const int v_per = (p.vn + gridDim.y - 1) / gridDim.y;
   const int v_lo = blockIdx.y * v_per, v_hi = min(p.vn, v_lo + v_per);
-  if (blockIdx.y == 0)
+  if (blockIdx.y == 0) {
+    uint32_t* out = ws.fgpix + (size_t)b * HW;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int q0 = seg + k * 128 + lane * 4;
-    int o = ok[k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if ((flags[k] >> j) & 1u) {
-        const int px = q0 + j;
+    for (int g = 0; g < 16; ++g)
+      if ((mine >> g) & 1u) {
+        const int px = seg + g * 32 + lane;
         const int y = px / W, x = px - y * W;
-        out[o++] = ((uint32_t)y << 16) | (uint32_t)x;
+        out[wbase + pos[g]] = ((uint32_t)y << 16) | (uint32_t)x;
       }
   }
-  if (PLANAR && (flags[0] | flags[1] | flags[2] | flags[3])) {
-    // planar field: every (image, keypoint, component) plane is one contiguous, 64-byte-aligned H*W
-    // array (the NCHW network output); quads without foreground are not read at all
-    const float* base = vertex + (b / p.classes) * p.sb + seg + lane * 4;
-    float2* dst = ws.direct + (size_t)b * p.vn * HW;
-    if (!light) {
-      for (int v = v_lo; v < v_hi; ++v) {
-        const float* px = base + (long long)v * p.sv;
-        const float* py = px + p.sc;
-        float4 dx[4], dy[4];
+  if (PLANAR && __any_sync(FULL, mine != 0u)) {
+    // planar field: every (image, keypoint, component) plane is one contiguous H*W array (the NCHW network
+    // output): pixel px is element px of the plane.  Groups without foreground are not read at all.
+    const float* base = vertex + (b / p.classes) * p.sb + seg + lane;
+    float2* dst = ws.direct + (size_t)b * p.vn * HW + wbase;
+    // host-resident field (`light`): 8 loads in flight per thread instead of 32 -- plenty for PCIe
+    for (int v = v_lo; v < v_hi; ++v) {
+      const float* px = base + (long long)v * p.sv;
+      const float* py = px + p.sc;
+      float2* d = dst + (size_t)v * HW;
+      if (!light) {
+        float fx[16], fy[16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (flags[k]) {
-            dx[k] = ldg_stream_f4(reinterpret_cast<const float4*>(px + k * 128));
-            dy[k] = ldg_stream_f4(reinterpret_cast<const float4*>(py + k * 128));
-          }
-        float2* d = dst + (size_t)v * HW;
+        for (int g = 0; g < 16; ++g)
+          if ((mine >> g) & 1u) { fx[g] = ldg_stream(px + g * 32); fy[g] = ldg_stream(py + g * 32); }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float fx[4] = {dx[k].x, dx[k].y, dx[k].z, dx[k].w};
-          const float fy[4] = {dy[k].x, dy[k].y, dy[k].z, dy[k].w};
-          int o = ok[k];
+        for (int g = 0; g < 16; ++g)
+          if ((mine >> g) & 1u) d[pos[g]] = make_float2(fx[g], fy[g]);
+      } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if ((flags[k] >> j) & 1u) d[o++] = make_float2(fx[j], fy[j]);
-        }
-      }
-    } else {
-      // host-resident field: two loads in flight per thread are plenty for PCIe and keep the SM's
-      // load/store queues free for the voting kernel that shares the SM
-#pragma unroll 1
-      for (int v = v_lo; v < v_hi; ++v) {
-        const float* px = base + (long long)v * p.sv;
-        const float* py = px + p.sc;
-        float2* d = dst + (size_t)v * HW;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          if (!flags[k]) continue;
-          const float4 dx = ldg_stream_f4(reinterpret_cast<const float4*>(px + k * 128));
-          const float4 dy = ldg_stream_f4(reinterpret_cast<const float4*>(py + k * 128));
-          const float fx[4] = {dx.x, dx.y, dx.z, dx.w}, fy[4] = {dy.x, dy.y, dy.z, dy.w};
-          int o = ok[k];
+        for (int g0 = 0; g0 < 16; g0 += 4) {
+          float fx[4], fy[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if ((flags[k] >> j) & 1u) d[o++] = make_float2(fx[j], fy[j]);
+          for (int g = 0; g < 4; ++g)
+            if ((mine >> (g0 + g)) & 1u) { fx[g] = ldg_stream(px + (g0 + g) * 32); fy[g] = ldg_stream(py + (g0 + g) * 32); }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if ((mine >> (g0 + g)) & 1u) d[pos[g0 + g]] = make_float2(fx[g], fy[g]);
         }
       }
     }
@@ -1367,8 +1322,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     EPB_RETURN_IF(check_launch());
   }
   // planar field (NCHW network output seen through vertex_layer_reshape): gather fused into the scatter
-  const bool planar = p.sx == 1 && p.sy == p.W && (HW % 16) == 0 && (p.sb % 16) == 0 && (p.sv % 16) == 0 &&
-                      (p.sc % 16) == 0 && (reinterpret_cast<uintptr_t>(io->vertex) & 63) == 0;
+  const bool planar = p.sx == 1 && p.sy == p.W;   // pixel px of a plane is element px: scalar, line-coalesced reads
   if (planar) {
     cudaPointerAttributes attr;
     const bool host_field = cudaPointerGetAttributes(&attr, io->vertex) == cudaSuccess && attr.type == cudaMemoryTypeHost;

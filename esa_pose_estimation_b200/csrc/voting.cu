@@ -296,17 +296,30 @@ mask_scan_kernel(int T, int phase, int min_num, int max_num, int allow_sub, Work
 __global__ void rng_offsets_kernel(int B, int rounds, unsigned long long base, unsigned long long inc_u,
                                    unsigned long long inc_r, Workspace ws,
                                    unsigned long long* consumed, unsigned long long* state) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: exclusive scan over the batch of what each image consumes, 32 images per step
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   if (state) base = *state;   // offset chained on the device from the previous run (batch chunks)
   unsigned long long o = base;
-  for (int b = 0; b < B; ++b) {
-    ws.off_u[b] = o;
-    if (ws.sub[b]) o += inc_u;
-    ws.off_r[b] = o;
-    if (ws.live[b]) o += inc_r * (unsigned long long)rounds;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    const int b = b0 + lane;
+    const bool in = b < B;
+    const unsigned long long du = (in && ws.sub[b]) ? inc_u : 0ull;
+    const unsigned long long dr = (in && ws.live[b]) ? inc_r * (unsigned long long)rounds : 0ull;
+    unsigned long long incl = du + dr;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long up = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += up;
+    }
+    const unsigned long long before = o + incl - (du + dr);
+    if (in) { ws.off_u[b] = before; ws.off_r[b] = before + du; }
+    o += __shfl_sync(FULL, incl, 31);
   }
-  if (consumed) *consumed = o - base;
-  if (state) *state = o;
+  if (lane == 0) {
+    if (consumed) *consumed = o - base;
+    if (state) *state = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

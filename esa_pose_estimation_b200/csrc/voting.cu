@@ -1420,12 +1420,13 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     // held two below full occupancy there (unused dynamic shared memory is the occupancy knob; measured:
     // gather 0.75 -> 0.58 ms per chunk under a concurrent vote, vote 0.68 -> 0.61 ms).
     size_t pad = 0;
-    if (p.stage == EPB_STAGE_VOTE && occ >= 4) {
+    if (p.stage == EPB_STAGE_VOTE && occ >= 6) {   // (kernels already at <= 5 CTAs/SM leave that room anyway)
       static const int knob = [] { const char* e = getenv("EPB_VOTE_HEADROOM"); return e ? atoi(e) : 2; }();
       const int want = occ - knob;
       const size_t per_sm = 227 * 1024, used = sizeof(VoteSmem) + 1024;
       if (knob > 0 && want >= 1 && per_sm / (size_t)want > used) pad = per_sm / (size_t)(want + 1) + 1024 > used
                                                                           ? per_sm / (size_t)(want + 1) + 1024 - used : 0;
+      if (pad + used > 48 * 1024) pad = 0;       // stay within the default dynamic shared memory limit
     }
     ProfScope ps(PROF_VOTE_COUNT, s);
     if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);

@@ -91,3 +91,19 @@ def test_host_field_chunked_pipeline_equals_device_run(cuda_dev):
         assert torch.equal(out["kpts"].view(torch.int32), ref["kpts"].view(torch.int32)), chunks
         live = torch.ones(B, dtype=torch.bool); live[3] = False
         assert torch.equal(out["pose7"][live].view(torch.int32), ref["pose7"][live].view(torch.int32)), chunks
+
+
+def test_host_pipeline_with_many_hypotheses(cuda_dev):
+    """Split (gather / vote) runs with > 512 hypotheses per keypoint (the 8-hypotheses-per-thread kernel,
+    whose occupancy leaves the gather stage room without the shared-memory padding)."""
+    from esa_pose_estimation_b200 import pipeline, ransac_voting_gpu as rv
+    B, vn, S, hn = 16, 3, 64, 1024
+    mask, vertex, _ = make_vertex_field(73, B, S, S, vn, 0.4, noise_deg=1.5)
+    model = torch.from_numpy(tango_model(vn + 3, seed=9)[:vn]).to(cuda_dev)
+    K = torch.from_numpy(np.array([[120.0, 0, 32], [0, 120.0, 32], [0, 0, 1]])).to(cuda_dev)
+    m_h, v_h = torch.from_numpy(mask).pin_memory(), torch.from_numpy(vertex).pin_memory()
+    torch.manual_seed(9)
+    ref = rv.ransac_voting_layer_v3(m_h.to(cuda_dev), rv.vertex_layer_reshape(v_h.to(cuda_dev)), hn)
+    torch.manual_seed(9)
+    out = pipeline.poses_from_vertex(m_h, rv.vertex_layer_reshape(v_h), model, K, round_hyp_num=hn, chunks=4)
+    assert torch.equal(out["kpts"].view(torch.int32), ref.view(torch.int32))

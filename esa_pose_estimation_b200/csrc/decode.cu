@@ -285,12 +285,8 @@ extern "C" int epb_refine_keypoints_dark(const float* hm, int n_maps, int H, int
   if (band > 64) band = 64;
   if (band < 1) return EPB_ERR_INVALID;
   const size_t smem = (size_t)(band + 10) * W * 12;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(dark_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-      return check_api(cudaGetLastError());
-    attr_set = true;
-  }
+  // per device and cheap: set on every call (one process may drive several devices)
+  EPB_RETURN_IF(check_api(cudaFuncSetAttribute(dark_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)));
   dark_refine_kernel<<<n_maps, 256, smem, (cudaStream_t)stream>>>(hm, n_maps, H, W, band, g, xy);
   return check_launch();
 }

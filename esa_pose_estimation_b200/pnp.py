@@ -199,6 +199,10 @@ def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix, init_rt=Non
     ([6] angle-axis, t) is given.  Both converge to the same LM minimiser on well-posed input."""
     pn = points_2d.shape[0]
     assert points_3d.shape[0] == pn and pn >= 4
+    if pn == 4 and init_rt is None:
+        # extend_utils.py:91-95 returns cv2's P3P pose itself for exactly four points; that third-party
+        # solver is not restated here and EPnP-RANSAC needs five: refuse rather than return garbage
+        raise NotImplementedError("uncertainty_pnp with exactly 4 points needs init_rt (cv2 P3P is not restated)")
     dev = _device()
     p2, p3, w = _f64(points_2d, dev)[None], _f64(points_3d, dev)[None], _f64(weights_2d, dev)[None]
     K = _f64(camera_matrix, dev)

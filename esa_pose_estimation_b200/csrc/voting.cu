@@ -548,12 +548,6 @@ __device__ __forceinline__ float half2(f32x2 v, int hi) {
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
 }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
-__device__ __forceinline__ float mul_sat(float a, float b) {
-  float r; asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
-}
 
 constexpr int VOTE_THREADS = 128;
 constexpr int VOTE_TILE = 256;  // records per smem tile

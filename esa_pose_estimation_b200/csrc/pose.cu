@@ -30,6 +30,10 @@ struct WarpScratch {
   double L[6][10];
   double vs[4][12];  // the four null-space vectors, ascending eigenvalue
   int order[12];
+  // Jacobi pair tables, copied from constant memory once per eigen-solve: they are indexed with
+  // lane-dependent subscripts, which the constant cache serialises (one address per cycle) -- measured
+  // ~1900 cycles per Jacobi step with the tables in __constant__ memory
+  unsigned char jp[11][6], jq[11][6], ba[15], bb[15];
 };
 
 struct Cam { double fu, fv, uc, vc; };
@@ -122,9 +126,12 @@ __constant__ unsigned char kBA[15] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 
 __constant__ unsigned char kBB[15] = {1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
 
 __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
+  for (int e = lane; e < 66; e += 32) { ws.jp[e / 6][e % 6] = kJP[e / 6][e % 6]; ws.jq[e / 6][e % 6] = kJQ[e / 6][e % 6]; }
+  if (lane < 15) { ws.ba[lane] = kBA[lane]; ws.bb[lane] = kBB[lane]; }
   for (int e = lane; e < 144; e += 32) ws.V[e / 12][e % 12] = (e / 12 == e % 12) ? 1.0 : 0.0;
   __syncwarp();
-  double* cs = ws.S;  // [6][4]: c, s, t, apq of the current step (S is free during the eigen-solve)
+  double* cs = ws.S;  // [6][4]: c, s of the current step (S is free during the eigen-solve)
+  double off_prev = INFINITY;
   for (int sweep = 0; sweep < 30; ++sweep) {
     double off = 0;
     for (int e = lane; e < 144; e += 32) {
@@ -137,32 +144,52 @@ __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
     // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the
     // null-space vectors are what EPnP needs); exact null spaces fall through to the absolute test
     if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
+    // rounding floor: once the off-diagonal norm is at rounding level of the matrix scale AND a sweep no
+    // longer halves it, there is nothing left to remove.  Rank-deficient M^T M (the 5-point RANSAC samples: two exact null
+    // vectors, dmin at rounding level) can never meet the relative test above and used to run all 30 sweeps.
+    {
+      double tr = 0;
+      for (int i = 0; i < 12; ++i) tr += fabs(ws.A[i][i]);
+      if (off < 1e-28 * tr * tr && off > 0.5 * off_prev) break;   // |off-diagonal| < 1e-14 of the scale, and stalled
+    }
+    off_prev = off;
     for (int step = 0; step < 11; ++step) {
       // --- rotation angles of the 6 disjoint pairs
       if (lane < 6) {
-        const int p = kJP[step][lane], q = kJQ[step][lane];
+        const int p = ws.jp[step][lane], q = ws.jq[step][lane];
         const double apq = ws.A[p][q];
-        double c = 1.0, s = 0.0, t = 0.0;
+        double c = 1.0, s = 0.0;
         if (apq != 0.0) {
-          // tan of the rotation angle: t = sgn / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq),
-          // rewritten without theta as sgn(alpha apq) |apq| / (|alpha| + hypot(alpha, apq)).  Jacobi is
-          // self-correcting in t (an inexact t leaves a residual a_pq that the next sweep removes, the
-          // rotation stays orthogonal as long as c^2 + s^2 = 1), so t is evaluated in float32 with the fast
-          // reciprocal / square root and only c = rsqrt(1 + t^2) in float64: one long FP64 operation on
-          // the critical path of each of the ~80 steps instead of two divisions and two square roots.
+          // Rotation that annihilates a_pq: the small root of  b t^2 + 2 a t - b = 0  with a = (aqq - app)/2,
+          // b = a_pq (t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) in the textbook form).  The root and
+          // c = (1 + t^2)^(-1/2) are seeded in float32 with the fast reciprocal / square roots and polished by
+          // one Newton step each in float64 (relative error ~1e-14), then (c, s) are renormalised to
+          // c^2 + s^2 = 1 within rounding; the (p,q) block is transformed with those very (c, s) below (no
+          // "a_pq := 0" shortcut), so the update is an exact orthogonal similarity and any residual a_pq is
+          // removed by the next sweep.  This takes the two FP64 divisions and two square roots of the textbook
+          // formula off the critical path of the ~80 steps.
           const double alpha = 0.5 * (ws.A[q][q] - ws.A[p][p]);
           const double scale = fmax(fabs(alpha), fabs(apq));
           // exact power-of-two rescale into float32 range (exponent arithmetic, no division)
           const int e = ((__double2hiint(scale) >> 20) & 0x7ff) - 1023;
           const double inv = __hiloint2double((1023 - max(min(e, 1022), -1022)) << 20, 0);
-          const float af = (float)(fabs(alpha) * inv), bf = (float)(fabs(apq) * inv);
+          const double a = alpha * inv, b = apq * inv;
+          const float af = fabsf((float)a), bf = fabsf((float)b);
           const float tf = __fdividef(bf, af + __fsqrt_rn(af * af + bf * bf));
+          const float cf = rsqrtf(__fmaf_rn(tf, tf, 1.0f));
           const bool pos = alpha == 0.0 || ((alpha > 0) == (apq > 0));   // sign of theta (theta = +-0 counts as +)
-          t = pos ? (double)tf : -(double)tf;
-          c = rsqrt(t * t + 1.0);
-          s = t * c;
+          const double t0 = pos ? (double)tf : -(double)tf;
+          const double res = fma(b * t0, t0, fma(2.0 * a, t0, -b));       // f(t0)
+          const double der = 2.0 * fma(b, t0, a);                          // f'(t0) = +-2 hypot(a, b) near the root
+          const double t1 = der != 0.0 ? t0 - res * (double)__frcp_rn((float)der) : t0;
+          const double u = fma(t1, t1, 1.0);
+          const double c0 = (double)cf;
+          const double c1 = c0 * fma(-0.5 * u, c0 * c0, 1.5);              // Newton step of y = u^(-1/2)
+          const double fix = fma(-0.5, fma(c1 * c1, u, -1.0), 1.0);        // renormalise: c^2 + s^2 = c1^2 u
+          c = c1 * fix;
+          s = t1 * c;
         }
-        cs[4 * lane] = c; cs[4 * lane + 1] = s; cs[4 * lane + 2] = t; cs[4 * lane + 3] = apq;
+        cs[4 * lane] = c; cs[4 * lane + 1] = s;
       }
       __syncwarp();
       // --- read phase: everything a lane will write is computed into registers first
@@ -173,8 +200,8 @@ __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
         blk_r[k] = -1; blk_c[k] = 0; blk_val[k] = 0.0;
         if (task < 60) {
           const int blk = task >> 2, e = task & 3, u = e >> 1, w = e & 1;
-          const int a = kBA[blk], b = kBB[blk];
-          const int pa = kJP[step][a], qa = kJQ[step][a], pb = kJP[step][b], qb = kJQ[step][b];
+          const int a = ws.ba[blk], b = ws.bb[blk];
+          const int pa = ws.jp[step][a], qa = ws.jq[step][a], pb = ws.jp[step][b], qb = ws.jq[step][b];
           const double ca = cs[4 * a], sa = cs[4 * a + 1], cb = cs[4 * b], sb = cs[4 * b + 1];
           const double b00 = ws.A[pa][pb], b01 = ws.A[pa][qb], b10 = ws.A[qa][pb], b11 = ws.A[qa][qb];
           // T = Ra^T B (row u), then Bn = T Rb (column w);  Ra = [[ca, sa], [-sa, ca]]
@@ -192,19 +219,23 @@ __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
         v_i[k] = -1; v_pp[k] = 0; v_qq[k] = 0; v_p[k] = 0.0; v_q[k] = 0.0;
         if (task < 72) {
           const int i = task / 6, a = task - 6 * i;
-          const int p = kJP[step][a], q = kJQ[step][a];
+          const int p = ws.jp[step][a], q = ws.jq[step][a];
           const double c = cs[4 * a], s = cs[4 * a + 1];
           const double vp = ws.V[i][p], vq = ws.V[i][q];
           v_p[k] = c * vp - s * vq; v_q[k] = s * vp + c * vq;
           v_i[k] = i; v_pp[k] = p; v_qq[k] = q;
         }
       }
-      double d_pp = 0, d_qq = 0; int d_p = -1, d_q = 0;
+      double d_pp = 0, d_qq = 0, d_pq = 0; int d_p = -1, d_q = 0;
       if (lane < 6) {
-        d_p = kJP[step][lane]; d_q = kJQ[step][lane];
-        const double t = cs[4 * lane + 2], apq = cs[4 * lane + 3];
-        d_pp = ws.A[d_p][d_p] - t * apq;
-        d_qq = ws.A[d_q][d_q] + t * apq;
+        // the (p,q) block under the same rotation: J^T [[app, apq], [apq, aqq]] J, J = [[c, s], [-s, c]]
+        d_p = ws.jp[step][lane]; d_q = ws.jq[step][lane];
+        const double c = cs[4 * lane], s = cs[4 * lane + 1];
+        const double app = ws.A[d_p][d_p], aqq = ws.A[d_q][d_q], apq = ws.A[d_p][d_q];
+        const double cc = c * c, ss = s * s, sc2 = 2.0 * c * s;
+        d_pp = cc * app - sc2 * apq + ss * aqq;
+        d_qq = ss * app + sc2 * apq + cc * aqq;
+        d_pq = c * s * (app - aqq) + (cc - ss) * apq;
       }
       __syncwarp();
       // --- write phase
@@ -214,7 +245,7 @@ __device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
 #pragma unroll
       for (int k = 0; k < 3; ++k)
         if (v_i[k] >= 0) { ws.V[v_i[k]][v_pp[k]] = v_p[k]; ws.V[v_i[k]][v_qq[k]] = v_q[k]; }
-      if (d_p >= 0) { ws.A[d_p][d_p] = d_pp; ws.A[d_q][d_q] = d_qq; ws.A[d_p][d_q] = 0.0; ws.A[d_q][d_p] = 0.0; }
+      if (d_p >= 0) { ws.A[d_p][d_p] = d_pp; ws.A[d_q][d_q] = d_qq; ws.A[d_p][d_q] = d_pq; ws.A[d_q][d_p] = d_pq; }
       __syncwarp();
     }
   }

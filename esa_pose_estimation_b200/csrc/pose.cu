@@ -30,10 +30,6 @@ struct WarpScratch {
   double L[6][10];
   double vs[4][12];  // the four null-space vectors, ascending eigenvalue
   int order[12];
-  // Jacobi pair tables, copied from constant memory once per eigen-solve: they are indexed with
-  // lane-dependent subscripts, which the constant cache serialises (one address per cycle) -- measured
-  // ~1900 cycles per Jacobi step with the tables in __constant__ memory
-  unsigned char jp[11][6], jq[11][6], ba[15], bb[15];
 };
 
 struct Cam { double fu, fv, uc, vc; };
@@ -111,142 +107,117 @@ __device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[
   }
 }
 
-// Parallel-order (Brent-Luk round robin) Jacobi eigen-decomposition of the symmetric 12x12 in shared
-// memory: each of the 11 steps of a sweep applies 6 disjoint rotations at once, A <- J^T A J, with the
-// work spread over all 32 lanes (60 off-diagonal block elements + 72 eigenvector row updates per
-// step).  Every off-diagonal 2x2 block is computed once and mirrored, so A stays exactly symmetric.
-// Eigenvectors end up in the columns of V.  (Validated in numpy, see oracle/epnp_port.py notes.)
-__constant__ unsigned char kJP[11][6] = {{0, 2, 4, 6, 8, 10}, {0, 1, 2, 4, 6, 8}, {0, 3, 1, 2, 4, 6}, {0, 5, 3, 1, 2, 4},
-                                         {0, 7, 5, 3, 1, 2},  {0, 9, 7, 5, 3, 1}, {0, 8, 6, 4, 2, 1}, {0, 6, 4, 2, 1, 3},
-                                         {0, 4, 2, 1, 3, 5},  {0, 2, 1, 3, 5, 7}, {0, 1, 3, 5, 7, 9}};
-__constant__ unsigned char kJQ[11][6] = {{1, 3, 5, 7, 9, 11},  {3, 5, 7, 9, 11, 10}, {5, 7, 9, 11, 10, 8}, {7, 9, 11, 10, 8, 6},
-                                         {9, 11, 10, 8, 6, 4}, {11, 10, 8, 6, 4, 2}, {10, 11, 9, 7, 5, 3}, {8, 10, 11, 9, 7, 5},
-                                         {6, 8, 10, 11, 9, 7}, {4, 6, 8, 10, 11, 9}, {2, 4, 6, 8, 10, 11}};
-__constant__ unsigned char kBA[15] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4};
-__constant__ unsigned char kBB[15] = {1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
-
-__device__ void jacobi_eigh12(WarpScratch& ws, int lane) {
-  for (int e = lane; e < 66; e += 32) { ws.jp[e / 6][e % 6] = kJP[e / 6][e % 6]; ws.jq[e / 6][e % 6] = kJQ[e / 6][e % 6]; }
-  if (lane < 15) { ws.ba[lane] = kBA[lane]; ws.bb[lane] = kBB[lane]; }
-  for (int e = lane; e < 144; e += 32) ws.V[e / 12][e % 12] = (e / 12 == e % 12) ? 1.0 : 0.0;
-  __syncwarp();
-  double* cs = ws.S;  // [6][4]: c, s of the current step (S is free during the eigen-solve)
+// Parallel-order (round robin) Jacobi eigen-decomposition of the symmetric 12x12, REGISTER resident:
+// lane l < 12 holds the column at position l of A, lane 12 + l the column at position l of V (the
+// eigenvectors).  Every step rotates the six pairs of neighbouring positions (2k, 2k+1) at once,
+// A <- J^T A J, V <- V J, and then moves rows and columns by the fixed "tournament" permutation (position
+// 0 stays, the others go round), so that after 11 steps every pair of columns has met once and the code
+// of a step never changes: partner = lane ^ 1, all register indices static, one short loop body.  The
+// column half of the update is one exchange of the two columns of a pair (warp shuffle), the row half is
+// local to every column once the six (c, s) have been broadcast.  No shared-memory round trips and no
+// barriers inside a sweep.  Eigenvalue at position x <-> eigenvector in the V column at position x.
+__device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
+  const bool isA = lane < 12, isV = lane >= 12 && lane < 24;
+  const int pos = isA ? lane : (isV ? lane - 12 : 0);
+  // tournament permutation pi = {0,2,4,1,6,3,8,5,10,7,11,9}: what is at position x moves to pi[x];
+  // kInv[y] = the position whose content arrives at y
+  const int inv_pos = (int)((0xa8b694725130ull >> (4 * pos)) & 15ull);
+  const int from_lane = (isV ? 12 : 0) + inv_pos;
+  double a[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) a[i] = isA ? ws.A[i][pos] : ((isV && i == pos) ? 1.0 : 0.0);
   double off_prev = INFINITY;
   for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0;
-    for (int e = lane; e < 144; e += 32) {
-      const int r = e / 12, c = e % 12;
-      if (r < c) { const double x = ws.A[r][c]; off += x * x; }
-    }
-    off = warp_sum(off);
-    double dmin = INFINITY;
-    for (int i = 0; i < 12; ++i) dmin = fmin(dmin, fabs(ws.A[i][i]));
+    double dg = 0, off = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { if (i == pos) dg = a[i]; else off += a[i] * a[i]; }
+    off = 0.5 * warp_sum(isA ? off : 0.0);
+    double dmin = isA ? fabs(dg) : INFINITY;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, m));
+    const double tr = warp_sum(isA ? fabs(dg) : 0.0);
     // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the
     // null-space vectors are what EPnP needs); exact null spaces fall through to the absolute test
     if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
     // rounding floor: once the off-diagonal norm is at rounding level of the matrix scale AND a sweep no
-    // longer halves it, there is nothing left to remove.  Rank-deficient M^T M (the 5-point RANSAC samples: two exact null
-    // vectors, dmin at rounding level) can never meet the relative test above and used to run all 30 sweeps.
-    {
-      double tr = 0;
-      for (int i = 0; i < 12; ++i) tr += fabs(ws.A[i][i]);
-      if (off < 1e-28 * tr * tr && off > 0.5 * off_prev) break;   // |off-diagonal| < 1e-14 of the scale, and stalled
-    }
+    // longer halves it, there is nothing left to remove (rank-deficient M^T M of the 5-point samples)
+    if (off < 1e-28 * tr * tr && off > 0.5 * off_prev) break;
     off_prev = off;
+#pragma unroll 1
     for (int step = 0; step < 11; ++step) {
-      // --- rotation angles of the 6 disjoint pairs
-      if (lane < 6) {
-        const int p = ws.jp[step][lane], q = ws.jq[step][lane];
-        const double apq = ws.A[p][q];
-        double c = 1.0, s = 0.0;
-        if (apq != 0.0) {
-          // Rotation that annihilates a_pq: the small root of  b t^2 + 2 a t - b = 0  with a = (aqq - app)/2,
-          // b = a_pq (t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) in the textbook form).  The root and
-          // c = (1 + t^2)^(-1/2) are seeded in float32 with the fast reciprocal / square roots and polished by
-          // one Newton step each in float64 (relative error ~1e-14), then (c, s) are renormalised to
-          // c^2 + s^2 = 1 within rounding; the (p,q) block is transformed with those very (c, s) below (no
-          // "a_pq := 0" shortcut), so the update is an exact orthogonal similarity and any residual a_pq is
-          // removed by the next sweep.  This takes the two FP64 divisions and two square roots of the textbook
-          // formula off the critical path of the ~80 steps.
-          const double alpha = 0.5 * (ws.A[q][q] - ws.A[p][p]);
-          const double scale = fmax(fabs(alpha), fabs(apq));
-          // exact power-of-two rescale into float32 range (exponent arithmetic, no division)
-          const int e = ((__double2hiint(scale) >> 20) & 0x7ff) - 1023;
-          const double inv = __hiloint2double((1023 - max(min(e, 1022), -1022)) << 20, 0);
-          const double a = alpha * inv, b = apq * inv;
-          const float af = fabsf((float)a), bf = fabsf((float)b);
-          const float tf = __fdividef(bf, af + __fsqrt_rn(af * af + bf * bf));
-          const float cf = rsqrtf(__fmaf_rn(tf, tf, 1.0f));
-          const bool pos = alpha == 0.0 || ((alpha > 0) == (apq > 0));   // sign of theta (theta = +-0 counts as +)
-          const double t0 = pos ? (double)tf : -(double)tf;
-          const double res = fma(b * t0, t0, fma(2.0 * a, t0, -b));       // f(t0)
-          const double der = 2.0 * fma(b, t0, a);                          // f'(t0) = +-2 hypot(a, b) near the root
-          const double t1 = der != 0.0 ? t0 - res * (double)__frcp_rn((float)der) : t0;
-          const double u = fma(t1, t1, 1.0);
-          const double c0 = (double)cf;
-          const double c1 = c0 * fma(-0.5 * u, c0 * c0, 1.5);              // Newton step of y = u^(-1/2)
-          const double fix = fma(-0.5, fma(c1 * c1, u, -1.0), 1.0);        // renormalise: c^2 + s^2 = c1^2 u
-          c = c1 * fix;
-          s = t1 * c;
-        }
-        cs[4 * lane] = c; cs[4 * lane + 1] = s;
-      }
-      __syncwarp();
-      // --- read phase: everything a lane will write is computed into registers first
-      double blk_val[2]; int blk_r[2], blk_c[2];
+      const bool amP = (pos & 1) == 0;
+      // this column's diagonal element and its element in the partner's row
+      double dme = 0, apq = 0;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int task = lane + 32 * k;   // 60 tasks: 15 blocks x 4 elements
-        blk_r[k] = -1; blk_c[k] = 0; blk_val[k] = 0.0;
-        if (task < 60) {
-          const int blk = task >> 2, e = task & 3, u = e >> 1, w = e & 1;
-          const int a = ws.ba[blk], b = ws.bb[blk];
-          const int pa = ws.jp[step][a], qa = ws.jq[step][a], pb = ws.jp[step][b], qb = ws.jq[step][b];
-          const double ca = cs[4 * a], sa = cs[4 * a + 1], cb = cs[4 * b], sb = cs[4 * b + 1];
-          const double b00 = ws.A[pa][pb], b01 = ws.A[pa][qb], b10 = ws.A[qa][pb], b11 = ws.A[qa][qb];
-          // T = Ra^T B (row u), then Bn = T Rb (column w);  Ra = [[ca, sa], [-sa, ca]]
-          const double t0 = u == 0 ? ca * b00 - sa * b10 : sa * b00 + ca * b10;
-          const double t1 = u == 0 ? ca * b01 - sa * b11 : sa * b01 + ca * b11;
-          blk_val[k] = w == 0 ? t0 * cb - t1 * sb : t0 * sb + t1 * cb;
-          blk_r[k] = u == 0 ? pa : qa;
-          blk_c[k] = w == 0 ? pb : qb;
+      for (int i = 0; i < 12; ++i) { if (i == pos) dme = a[i]; if (i == (pos ^ 1)) apq = a[i]; }
+      const double doth = __shfl_xor_sync(FULL, dme, 1);              // the partner's diagonal element
+      double c = 1.0, s = 0.0;
+      if (isA && amP && apq != 0.0) {
+        // Rotation that annihilates a_pq: the small root of  b t^2 + 2 a t - b = 0  with a = (aqq - app)/2,
+        // b = a_pq (t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) in the textbook form).  The root and
+        // c = (1 + t^2)^(-1/2) are seeded in float32 with the fast reciprocal / square roots and polished by
+        // one Newton step each in float64 (relative error ~1e-14), then renormalised to c^2 + s^2 = 1 within
+        // rounding; A is transformed with those very (c, s) (an exact orthogonal similarity, no
+        // "a_pq := 0" shortcut), so any residual a_pq is removed by the next sweep.
+        const double alpha = 0.5 * (doth - dme);
+        const double scale = fmax(fabs(alpha), fabs(apq));
+        const int e = ((__double2hiint(scale) >> 20) & 0x7ff) - 1023;   // exact power-of-two rescale, no division
+        const double inv = __hiloint2double((1023 - max(min(e, 1022), -1022)) << 20, 0);
+        const double aa = alpha * inv, bb = apq * inv;
+        const float af = fabsf((float)aa), bf = fabsf((float)bb);
+        const float tf = __fdividef(bf, af + __fsqrt_rn(af * af + bf * bf));
+        const float cf = rsqrtf(__fmaf_rn(tf, tf, 1.0f));
+        const bool plus = alpha == 0.0 || ((alpha > 0) == (apq > 0));   // sign of theta (theta = +-0 counts as +)
+        const double t0 = plus ? (double)tf : -(double)tf;
+        const double res = fma(bb * t0, t0, fma(2.0 * aa, t0, -bb));    // f(t0)
+        const double der = 2.0 * fma(bb, t0, aa);                        // f'(t0) = +-2 hypot(a, b) near the root
+        const double t1 = der != 0.0 ? t0 - res * (double)__frcp_rn((float)der) : t0;
+        const double u = fma(t1, t1, 1.0);
+        const double c0 = (double)cf;
+        const double c1 = c0 * fma(-0.5 * u, c0 * c0, 1.5);             // Newton step of y = u^(-1/2)
+        const double fix = fma(-0.5, fma(c1 * c1, u, -1.0), 1.0);       // renormalise: c^2 + s^2 = c1^2 u
+        c = c1 * fix;
+        s = t1 * c;
+      }
+      // every lane takes the (c, s) of its pair from the A lane of the pair's first column
+      c = __shfl_sync(FULL, c, pos & ~1);
+      s = __shfl_sync(FULL, s, pos & ~1);
+      // column half: [col_p, col_q] <- [c col_p - s col_q, s col_p + c col_q]   (A and V alike)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const double o = __shfl_xor_sync(FULL, a[i], 1);
+        a[i] = amP ? fma(c, a[i], -s * o) : fma(s, o, c * a[i]);
+      }
+      // row half (A only): rows 2k, 2k+1 of every column <- J^T rows, with the (c, s) of pair k
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double ck = __shfl_sync(FULL, c, 2 * k), sk = __shfl_sync(FULL, s, 2 * k);
+        if (isA) {
+          const double rp = a[2 * k], rq = a[2 * k + 1];
+          a[2 * k] = fma(ck, rp, -sk * rq);
+          a[2 * k + 1] = fma(sk, rp, ck * rq);
         }
       }
-      double v_p[3], v_q[3]; int v_i[3], v_pp[3], v_qq[3];
+      // tournament move: rows of A (register renaming) and columns of A and V (lane exchange)
+      {
+        double bnew[12];
+        bnew[0] = a[0]; bnew[2] = a[1]; bnew[4] = a[2]; bnew[1] = a[3]; bnew[6] = a[4]; bnew[3] = a[5];
+        bnew[8] = a[6]; bnew[5] = a[7]; bnew[10] = a[8]; bnew[7] = a[9]; bnew[11] = a[10]; bnew[9] = a[11];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const int task = lane + 32 * k;   // 72 tasks: 12 rows of V x 6 pairs
-        v_i[k] = -1; v_pp[k] = 0; v_qq[k] = 0; v_p[k] = 0.0; v_q[k] = 0.0;
-        if (task < 72) {
-          const int i = task / 6, a = task - 6 * i;
-          const int p = ws.jp[step][a], q = ws.jq[step][a];
-          const double c = cs[4 * a], s = cs[4 * a + 1];
-          const double vp = ws.V[i][p], vq = ws.V[i][q];
-          v_p[k] = c * vp - s * vq; v_q[k] = s * vp + c * vq;
-          v_i[k] = i; v_pp[k] = p; v_qq[k] = q;
-        }
+        for (int i = 0; i < 12; ++i) a[i] = __shfl_sync(FULL, isA ? bnew[i] : a[i], from_lane);
       }
-      double d_pp = 0, d_qq = 0, d_pq = 0; int d_p = -1, d_q = 0;
-      if (lane < 6) {
-        // the (p,q) block under the same rotation: J^T [[app, apq], [apq, aqq]] J, J = [[c, s], [-s, c]]
-        d_p = ws.jp[step][lane]; d_q = ws.jq[step][lane];
-        const double c = cs[4 * lane], s = cs[4 * lane + 1];
-        const double app = ws.A[d_p][d_p], aqq = ws.A[d_q][d_q], apq = ws.A[d_p][d_q];
-        const double cc = c * c, ss = s * s, sc2 = 2.0 * c * s;
-        d_pp = cc * app - sc2 * apq + ss * aqq;
-        d_qq = ss * app + sc2 * apq + cc * aqq;
-        d_pq = c * s * (app - aqq) + (cc - ss) * apq;
-      }
-      __syncwarp();
-      // --- write phase
+    }
+  }
+  // eigenvalues to the diagonal of ws.A, eigenvectors to the columns of ws.V (11 moves per sweep bring
+  // every column back to a permuted but consistent position: value at position x <-> V column x)
+  {
+    double dg = 0;
 #pragma unroll
-      for (int k = 0; k < 2; ++k)
-        if (blk_r[k] >= 0) { ws.A[blk_r[k]][blk_c[k]] = blk_val[k]; ws.A[blk_c[k]][blk_r[k]] = blk_val[k]; }
+    for (int i = 0; i < 12; ++i) if (i == pos) dg = a[i];
+    if (isA) ws.A[pos][pos] = dg;
+    if (isV) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (v_i[k] >= 0) { ws.V[v_i[k]][v_pp[k]] = v_p[k]; ws.V[v_i[k]][v_qq[k]] = v_q[k]; }
-      if (d_p >= 0) { ws.A[d_p][d_p] = d_pp; ws.A[d_q][d_q] = d_qq; ws.A[d_p][d_q] = d_pq; ws.A[d_q][d_p] = d_pq; }
-      __syncwarp();
+      for (int i = 0; i < 12; ++i) ws.V[i][pos] = a[i];
     }
   }
   __syncwarp();

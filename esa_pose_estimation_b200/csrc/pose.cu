@@ -434,9 +434,12 @@ __device__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int fir
   double pw0[3] = {c0[0], c0[1], c0[2]};
 
   best.err = INFINITY;
-#pragma unroll 1
-  for (int cand = 0; cand < 3; ++cand) {
-    double be[4] = {0, 0, 0, 0};
+  // The three beta initialisations and their Gauss-Newton refinements are independent and lane-redundant
+  // scalar work: lane l carries candidate l % 3, so the 3 x 5 Gauss-Newton solves run side by side
+  // (only the three different initial solves diverge); the betas are then broadcast per candidate.
+  double be[4] = {0, 0, 0, 0};
+  {
+    const int cand = lane % 3;
     if (cand == 0) {          // [B11 B12 B13 B14]
       double a[6][4], b[6], x[4];
 #pragma unroll
@@ -485,8 +488,14 @@ __device__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int fir
 #pragma unroll
       for (int k = 0; k < 4; ++k) be[k] += x[k];
     }
+  }
+#pragma unroll 1
+  for (int cand = 0; cand < 3; ++cand) {
+    double bc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bc[k] = __shfl_sync(FULL, be[k], cand);   // lane `cand` carries candidate `cand`
     PoseRT cur;
-    compute_r_and_t(ws, be, al, pw, u, v, active, n, first_lane, pw0, cam, cur);
+    compute_r_and_t(ws, bc, al, pw, u, v, active, n, first_lane, pw0, cam, cur);
     if (cand == 0 || cur.err < best.err) best = cur;
   }
 }

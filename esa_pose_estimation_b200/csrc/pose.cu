@@ -287,37 +287,51 @@ __device__ void lstsq6(double (&a)[6][N], double (&b)[6], double (&x)[N]) {
 // ------------------------------------------------------------------------------ EPnP
 struct PoseRT { double R[9]; double t[3]; double err; };
 
-__device__ void compute_r_and_t(const WarpScratch& ws, const double be[4], const double al[4],
-                                const double pw[3], double u, double v, bool active, int n,
-                                int first_lane, const double pw0[3], const Cam& cam, PoseRT& out) {
-  double ccs[4][3];
+// The three candidates at once: the per-point sums of all three are reduced interleaved (one reduction
+// latency instead of three), the 3x3 SVD / rotation / translation of candidate c is computed by the lanes
+// with lane % 3 == c (three different problems side by side instead of one after the other, lane-redundant
+// scalar work), and every point lane then scores all three poses.  Same arithmetic per candidate as
+// compute_r_and_t; the pose with the smallest mean reprojection error wins, ties keep the lower index.
+__device__ void compute_r_and_t3(const WarpScratch& ws, const double be[4], const double al[4],
+                                 const double pw[3], double u, double v, bool active, int n, int first_lane,
+                                 const double pw0[3], const Cam& cam, int lane, PoseRT& best) {
+  const int mine = lane % 3;
+  double abt[9], pc0m[3];
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    double bc[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 4; ++k) bc[k] = __shfl_sync(FULL, be[k], c);   // lane c carries candidate c
+    double pc[3] = {0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
-      ccs[j][k] = be[0] * ws.vs[0][3 * j + k] + be[1] * ws.vs[1][3 * j + k] +
-                  be[2] * ws.vs[2][3 * j + k] + be[3] * ws.vs[3][3 * j + k];
-  double pc[3];
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-    pc[k] = al[0] * ccs[0][k] + al[1] * ccs[1][k] + al[2] * ccs[2][k] + al[3] * ccs[3][k];
-  const double z0 = __shfl_sync(FULL, pc[2], first_lane);
-  if (z0 < 0.0) {
+      for (int k = 0; k < 3; ++k)
+        pc[k] += al[j] * (bc[0] * ws.vs[0][3 * j + k] + bc[1] * ws.vs[1][3 * j + k] +
+                          bc[2] * ws.vs[2][3 * j + k] + bc[3] * ws.vs[3][3 * j + k]);
+    const double z0 = __shfl_sync(FULL, pc[2], first_lane);
+    if (z0 < 0.0) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) pc[k] = -pc[k];
+      for (int k = 0; k < 3; ++k) pc[k] = -pc[k];
+    }
+    double pc0[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pc0[k] = warp_sum(active ? pc[k] : 0.0) / n;
+    double sum[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        sum[3 * j + k] = warp_sum(active ? (pc[j] - pc0[j]) * (pw[k] - pw0[k]) : 0.0);
+    if (mine == c) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) abt[i] = sum[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) pc0m[i] = pc0[i];
+    }
   }
-  double pc0[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) pc0[k] = warp_sum(active ? pc[k] : 0.0) / n;
-  double abt[9];
-#pragma unroll
-  for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      abt[3 * j + k] = warp_sum(active ? (pc[j] - pc0[j]) * (pw[k] - pw0[k]) : 0.0);
-  double w[3], ut[9], vt[9];
+  double w[3], ut[9], vt[9], R[9], t[3];
   svd3_cv(abt, w, ut, vt);
-  double* R = out.R;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -327,12 +341,22 @@ __device__ void compute_r_and_t(const WarpScratch& ws, const double be[4], const
                      R[2] * R[4] * R[6] - R[1] * R[3] * R[8] - R[0] * R[5] * R[7];
   if (det < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) out.t[i] = pc0[i] - (R[3 * i] * pw0[0] + R[3 * i + 1] * pw0[1] + R[3 * i + 2] * pw0[2]);
-  const double xc = R[0] * pw[0] + R[1] * pw[1] + R[2] * pw[2] + out.t[0];
-  const double yc = R[3] * pw[0] + R[4] * pw[1] + R[5] * pw[2] + out.t[1];
-  const double inv_z = 1.0 / (R[6] * pw[0] + R[7] * pw[1] + R[8] * pw[2] + out.t[2]);
-  const double du = u - (cam.uc + cam.fu * xc * inv_z), dv = v - (cam.vc + cam.fv * yc * inv_z);
-  out.err = warp_sum(active ? sqrt(du * du + dv * dv) : 0.0) / n;
+  for (int i = 0; i < 3; ++i) t[i] = pc0m[i] - (R[3 * i] * pw0[0] + R[3 * i + 1] * pw0[1] + R[3 * i + 2] * pw0[2]);
+  best.err = INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 3; ++c) {
+    PoseRT cur;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) cur.R[i] = __shfl_sync(FULL, R[i], c);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cur.t[i] = __shfl_sync(FULL, t[i], c);
+    const double xc = cur.R[0] * pw[0] + cur.R[1] * pw[1] + cur.R[2] * pw[2] + cur.t[0];
+    const double yc = cur.R[3] * pw[0] + cur.R[4] * pw[1] + cur.R[5] * pw[2] + cur.t[1];
+    const double inv_z = 1.0 / (cur.R[6] * pw[0] + cur.R[7] * pw[1] + cur.R[8] * pw[2] + cur.t[2]);
+    const double du = u - (cam.uc + cam.fu * xc * inv_z), dv = v - (cam.vc + cam.fv * yc * inv_z);
+    cur.err = warp_sum(active ? sqrt(du * du + dv * dv) : 0.0) / n;
+    if (c == 0 || cur.err < best.err) best = cur;
+  }
 }
 
 // EPnP over the lanes flagged `active` (n = popcount >= 4).  All lanes return the same pose.
@@ -489,15 +513,7 @@ __device__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int fir
       for (int k = 0; k < 4; ++k) be[k] += x[k];
     }
   }
-#pragma unroll 1
-  for (int cand = 0; cand < 3; ++cand) {
-    double bc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) bc[k] = __shfl_sync(FULL, be[k], cand);   // lane `cand` carries candidate `cand`
-    PoseRT cur;
-    compute_r_and_t(ws, bc, al, pw, u, v, active, n, first_lane, pw0, cam, cur);
-    if (cand == 0 || cur.err < best.err) best = cur;
-  }
+  compute_r_and_t3(ws, be, al, pw, u, v, active, n, first_lane, pw0, cam, lane, best);
 }
 
 // cv::RNG (multiply-with-carry), seed (uint64)-1 as RANSACPointSetRegistrator::run uses

@@ -400,3 +400,35 @@ def test_counts_bit_exact_for_large_hypothesis_sets(cuda_dev, hn, rounds):
             hyp_o = ov.generate_hypothesis(direct, coords, idxs[bi, r])
             np.testing.assert_array_equal(hyp[bi, sl].view(np.int32), hyp_o.view(np.int32))
             np.testing.assert_array_equal(cnt[bi, sl], ov.vote_counts(direct, coords, hyp_o, 0.99))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_fused_driver_fuzz_against_oracle(cuda_dev, seed):
+    """Random shapes (odd sizes, tiny and full foregrounds, ragged batches, subsample on/off, both field
+    layouts, random thresholds): hypotheses and counts bit-exact, refined points within 1e-3 px."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    rng = np.random.default_rng(1000 + seed)
+    b = int(rng.integers(1, 5)); h = int(rng.integers(9, 90)); w = int(rng.integers(9, 90))
+    vn = int(rng.integers(1, 9)); hn = int(rng.choice([1, 7, 32, 100, 257, 512, 600]))
+    frac = float(rng.choice([0.02, 0.2, 0.6, 1.0])); thresh = float(rng.choice([0.999, 0.99, 0.9]))
+    kind = str(rng.choice(["structured", "randinit"]))
+    max_num = int(rng.choice([30000, max(6, h * w // 7)]))
+    mask, vertex, _ = make_vertex_field(2000 + seed, b, h, w, vn, frac, kind)
+    if b > 1:
+        mask[-1, : h // 2] = 0
+    vx = vertex_hwvn2(vertex)
+    idxs, selection, fn, sel = _idxs_for(mask, vx, hn, 1, max_num, 40 + seed)
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev)) if seed % 2 else torch.from_numpy(vx).to(cuda_dev)
+    kw = dict(idxs=torch.from_numpy(idxs).to(cuda_dev), selection=torch.from_numpy(selection).to(cuda_dev))
+    dbg = rv.voting_debug(_lib.VOTE_V4, torch.from_numpy(mask).to(cuda_dev), vert, hn, inlier_thresh=thresh,
+                          max_num=max_num, **kw)
+    hyp_o, cnt_o = ov.ransac_voting_hypothesis((mask != 0).astype(np.uint8), vx, hn, thresh, max_num=max_num,
+                                               idxs_fn=fn, selection_fn=sel)
+    live = np.array([(mask[i] != 0).sum() >= 5 for i in range(b)])
+    np.testing.assert_array_equal(dbg["hyp"].cpu().numpy()[live].view(np.int32), hyp_o[live].view(np.int32))
+    np.testing.assert_array_equal(dbg["counts"].cpu().numpy()[live], cnt_o[live])
+    p4_o, var_o = ov.ransac_voting_layer_v4(mask, vx, hn, inlier_thresh=thresh, max_num=max_num, idxs_fn=fn, selection_fn=sel)
+    pts = dbg["pts"].cpu().numpy()
+    ok = np.isfinite(p4_o).all(axis=-1) & np.isfinite(pts).all(axis=-1)       # singular refinements: NaN on both sides
+    assert (np.isfinite(p4_o).all(axis=-1) == np.isfinite(pts).all(axis=-1)).all()
+    np.testing.assert_allclose(pts[ok], p4_o[ok], rtol=1e-5, atol=1e-3)

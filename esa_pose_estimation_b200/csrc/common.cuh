@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/esa_pose_b200.h"
 
@@ -44,6 +45,36 @@ struct ProfScope {
   do {                                 \
     int _s = (expr);                   \
     if (_s != EPB_OK) return _s;       \
+  } while (0)
+
+// Shared-memory carve-out.  An SM's L1 / shared-memory split is fixed while any CTA is resident, and it is
+// chosen by whichever kernel lands on the empty SM first.  Our kernels run concurrently on several streams
+// (gather of the next batch chunk under the voting of the current one, pose solve under the next call's
+// voting); a kernel without shared memory that arrives first leaves the SM with a split in which only one
+// or two of vote_count's 16 KB CTAs fit, which slowed a voting chunk from 0.56 to 2.6 ms in the co-run
+// microbenchmark (tools/corun.py).  Every kernel of this library therefore asks for a large shared-memory
+// carve-out (60 % measured best end to end: 2.36 ms per batch vs 2.44 at 72 %, 2.57 at 100 %, 2.69 without);
+// none of them depends on L1 capacity (streaming loads, shared-memory tiles) except the compaction
+// scatter, which is handled at its launch site.
+inline int carveout_percent() {
+  static const int pct = [] { const char* e = getenv("EPB_CARVEOUT"); return e ? atoi(e) : 60; }();
+  return pct;
+}
+template <typename K>
+inline void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout,
+                       carveout_percent());
+}
+// runs `init` once per device and file
+#define EPB_INIT_ONCE_PER_DEVICE(init)                                   \
+  do {                                                                   \
+    static unsigned long long done_mask = 0;                             \
+    int dev_ = 0;                                                        \
+    if (cudaGetDevice(&dev_) == cudaSuccess && dev_ >= 0 && dev_ < 64 &&  \
+        !((__atomic_load_n(&done_mask, __ATOMIC_ACQUIRE) >> dev_) & 1ull)) { \
+      init();                                                            \
+      __atomic_fetch_or(&done_mask, 1ull << dev_, __ATOMIC_RELEASE);     \
+    }                                                                    \
   } while (0)
 
 constexpr unsigned FULL = 0xffffffffu;

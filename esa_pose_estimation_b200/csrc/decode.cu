@@ -243,8 +243,16 @@ dark_refine_kernel(const float* __restrict__ hm, int n_maps, int H, int W, int b
 
 }  // namespace epb
 
+static void decode_kernel_attributes() {
+  using namespace epb;
+  prefer_max_shared(decode_kernel<32, 128>); prefer_max_shared(decode_kernel<256, 256>);
+  prefer_max_shared(refine_keypoints_kernel); prefer_max_shared(dark_refine_kernel);
+  cudaGetLastError();
+}
+
 extern "C" int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, int flags, float* xy,
                                    float* maxval, int32_t* idx, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(decode_kernel_attributes);
   using namespace epb;
   if (!hm || n_maps < 0 || H <= 0 || W <= 0 || (long long)H * W > 0x7fffffffLL) return EPB_ERR_INVALID;
   if (n_maps == 0) return EPB_OK;
@@ -261,6 +269,7 @@ extern "C" int epb_decode_heatmaps(const float* hm, int n_maps, int H, int W, in
 }
 
 extern "C" int epb_refine_keypoints(const float* hm, int n_maps, int H, int W, float* xy, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(decode_kernel_attributes);
   using namespace epb;
   if (!hm || !xy || n_maps < 0 || H <= 0 || W <= 0) return EPB_ERR_INVALID;
   if (n_maps == 0) return EPB_OK;
@@ -269,6 +278,7 @@ extern "C" int epb_refine_keypoints(const float* hm, int n_maps, int H, int W, f
 }
 
 extern "C" int epb_refine_keypoints_dark(const float* hm, int n_maps, int H, int W, float* xy, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(decode_kernel_attributes);
   using namespace epb;
   if (!hm || !xy || n_maps < 0 || H <= 0 || W <= 0 || W > 4096) return EPB_ERR_INVALID;
   if (n_maps == 0) return EPB_OK;

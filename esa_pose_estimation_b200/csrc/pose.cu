@@ -1084,10 +1084,18 @@ static inline void pose_launch_shape(int B, int* grid, int* block) {
   *grid = (B + warps - 1) / warps;
 }
 
+static void pose_kernel_attributes() {
+  prefer_max_shared(pnp_kernel); prefer_max_shared(lm_kernel); prefer_max_shared(pose_pack_kernel);
+  prefer_max_shared(rt34_to_rt6_kernel); prefer_max_shared(cov_to_weights_kernel); prefer_max_shared(pose_pipeline_kernel);
+  prefer_max_shared(esa_score_kernel);
+  cudaGetLastError();
+}
+
 extern "C" int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const double* p2d, const double* K,
                                    int K_batched, const int32_t* npts, int B, int n_max, double reproj_err,
                                    int max_iters, double confidence, double* rt34,
                                    unsigned long long* inlier_mask, int32_t* status, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!p3d || !p2d || !K || !rt34 || B < 0 || n_max <= 0 || n_max > 32 || max_iters < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   const int grid = B, block = 64;   // two warps per image: RANSAC + speculative all-point EPnP
@@ -1101,6 +1109,7 @@ extern "C" int epb_lm_refine(const double* p2d, const double* p3d, int p3d_batch
                              const double* K, int K_batched, const double* init_rt, const int32_t* npts,
                              int B, int n_max, double* result_rt, int32_t* iters, double* final_cost,
                              void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!p2d || !p3d || !w2d || !K || !init_rt || !result_rt || B < 0 || n_max <= 0 || n_max > 32)
     return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
@@ -1111,6 +1120,7 @@ extern "C" int epb_lm_refine(const double* p2d, const double* p3d, int p3d_batch
 }
 
 extern "C" int epb_pose_pack(const double* rt6, int B, float* pose7, double* rt34, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!rt6 || B < 0 || (!pose7 && !rt34)) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   pose_pack_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rt6, B, pose7, rt34);
@@ -1118,6 +1128,7 @@ extern "C" int epb_pose_pack(const double* rt6, int B, float* pose7, double* rt3
 }
 
 extern "C" int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!rt34 || !rt6 || B < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   rt34_to_rt6_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rt34, B, rt6);
@@ -1125,6 +1136,7 @@ extern "C" int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* str
 }
 
 extern "C" int epb_cov_to_weights(const float* cov, int n, double* w2d, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!cov || !w2d || n < 0) return EPB_ERR_INVALID;
   if (n == 0) return EPB_OK;
   cov_to_weights_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cov, n, w2d);
@@ -1135,6 +1147,7 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
                                  const double* rate, const double* p3d_model, const double* Kmat, int B,
                                  int K, int min_k, double sel_thresh, int weighted, float* pose7, double* rt6,
                                  double* epnp_rt34, int32_t* status, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!preds || !maxvals || !bbox_xy || !rate || !p3d_model || !Kmat || B < 0 || K <= 0 || K > 32)
     return EPB_ERR_INVALID;
   if (!pose7 && !rt6) return EPB_ERR_INVALID;
@@ -1149,6 +1162,7 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
 
 extern "C" int epb_esa_score(const float* pose7_pred, const float* pose7_gt, int B, double* score_t,
                              double* score_r, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!pose7_pred || !pose7_gt || B < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   esa_score_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pose7_pred, pose7_gt, B, score_t, score_r);

@@ -1250,6 +1250,17 @@ voting_for_hypothesis_vp_kernel(const float* __restrict__ direct, const float* _
 // ------------------------------------------------------------------------------------------
 using namespace epb;
 
+static void voting_kernel_attributes() {
+  prefer_max_shared(mask_count_kernel); prefer_max_shared(mask_scan_kernel); prefer_max_shared(rng_offsets_kernel);
+  prefer_max_shared(mask_scatter_kernel<true>); prefer_max_shared(mask_scatter_kernel<false>);
+  prefer_max_shared(field_gather_kernel); prefer_max_shared(hypothesis_kernel); prefer_max_shared(vote_items_kernel);
+  prefer_max_shared(vote_count_kernel<2>); prefer_max_shared(vote_count_kernel<4>); prefer_max_shared(vote_count_kernel<8>);
+  prefer_max_shared(counts_export_kernel); prefer_max_shared(winner_refine_kernel); prefer_max_shared(distribution_kernel);
+  prefer_max_shared(generate_hypothesis_kernel); prefer_max_shared(voting_for_hypothesis_kernel);
+  prefer_max_shared(generate_hypothesis_vp_kernel); prefer_max_shared(voting_for_hypothesis_vp_kernel);
+  cudaGetLastError();
+}
+
 static int g_vote_r_large = 4;  // hypotheses per thread when HN > 512 (measured at HN = 2048: 1.48 ms with 4, 1.66 ms with 8)
 
 static bool params_ok(const epb_voting_params* p) {
@@ -1283,6 +1294,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   if (!params_ok(pp) || !io || !workspace) return EPB_ERR_INVALID;
   const epb_voting_params p = virtual_batch(*pp);
   if (p.stage != EPB_STAGE_VOTE && (!io->mask || !io->vertex)) return EPB_ERR_INVALID;
+  EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
   if (p.rng_mode != EPB_RNG_PHILOX && !io->idxs) return EPB_ERR_INVALID;
   const bool is_layer = p.mode <= EPB_VOTE_V5 || p.mode == EPB_VOTE_V1 || p.mode == EPB_VOTE_V2;
   const bool is_dist = p.mode == EPB_VOTE_DISTRIBUTION || p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN;
@@ -1350,6 +1362,19 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     if (!host_field) {
       vsplit = vsplit_knob > 0 ? vsplit_knob : (work < 16LL * sm_n ? 2 : 1);
       if (vsplit > p.vn) vsplit = p.vn;
+    }
+    // The scatter is the kernel that shares SMs with vote_count in the host pipeline, where it must ask for a
+    // large shared-memory carve-out (common.cuh); alone on the device it is 20 % faster with the default
+    // split (88 vs 111 us), so the preference follows the kind of field (attribute read at launch).
+    {
+      static int current[64];   // per device: 0 unknown, 1 default split, 2 large carve-out (the call is not free)
+      const int want = host_field ? 2 : 1;
+      if (dev_id >= 0 && dev_id < 64 && current[dev_id] != want) {
+        cudaFuncSetAttribute(reinterpret_cast<const void*>(mask_scatter_kernel<true>),
+                             cudaFuncAttributePreferredSharedMemoryCarveout,
+                             host_field ? carveout_percent() : (int)cudaSharedmemCarveoutDefault);
+        current[dev_id] = want;
+      }
     }
     mask_scatter_kernel<true><<<dim3(g, vsplit), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p,
                                                               host_field && light_knob);
@@ -1448,6 +1473,7 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
 
 extern "C" int epb_generate_hypothesis(const float* direct, const float* coords, const int32_t* idxs,
                                        float* hypo, int tn, int vn, int hn, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
   if (!direct || !coords || !idxs || !hypo || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
   generate_hypothesis_kernel<<<(hn * vn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(direct, coords, idxs,
                                                                                   hypo, tn, vn, hn);
@@ -1457,6 +1483,7 @@ extern "C" int epb_generate_hypothesis(const float* direct, const float* coords,
 extern "C" int epb_voting_for_hypothesis(const float* direct, const float* coords, const float* hypo,
                                          uint8_t* inliers, int tn, int vn, int hn, float thresh,
                                          void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
   if (!direct || !coords || !hypo || !inliers || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
   if ((long long)hn * vn > 65535) {
     // grid.y limit: process in slabs of hypotheses
@@ -1477,6 +1504,7 @@ extern "C" int epb_voting_for_hypothesis(const float* direct, const float* coord
 extern "C" int epb_generate_hypothesis_vanishing_point(const float* direct, const float* coords,
                                                        const int32_t* idxs, float* hypo3, int tn, int vn,
                                                        int hn, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
   if (!direct || !coords || !idxs || !hypo3 || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
   generate_hypothesis_vp_kernel<<<(hn * vn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       direct, coords, idxs, hypo3, tn, vn, hn);
@@ -1486,6 +1514,7 @@ extern "C" int epb_generate_hypothesis_vanishing_point(const float* direct, cons
 extern "C" int epb_voting_for_hypothesis_vanishing_point(const float* direct, const float* coords,
                                                          const float* hypo3, uint8_t* inliers, int tn,
                                                          int vn, int hn, float thresh, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
   if (!direct || !coords || !hypo3 || !inliers || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
   if ((long long)hn * vn > 65535) return EPB_ERR_INVALID;
   voting_for_hypothesis_vp_kernel<<<dim3((tn + 255) / 256, hn * vn), 256, 0, (cudaStream_t)stream>>>(

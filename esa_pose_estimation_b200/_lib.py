@@ -16,7 +16,7 @@ STATUS_NAMES = {0: "EPB_OK", 1: "EPB_ERR_INVALID", 2: "EPB_ERR_CUDA", 3: "EPB_ER
                 4: "EPB_ERR_NO_DEVICE"}
 
 DECODE_REFINE, DECODE_ZERO_NONPOS = 1, 2
-VOTE_V3, VOTE_V4, VOTE_V5, VOTE_HYPOTHESIS, VOTE_DISTRIBUTION, VOTE_DISTRIBUTION_WITH_MEAN, VOTE_V1, VOTE_V2 = range(8)
+VOTE_V3, VOTE_V4, VOTE_V5, VOTE_HYPOTHESIS, VOTE_DISTRIBUTION, VOTE_DISTRIBUTION_WITH_MEAN, VOTE_V1, VOTE_V2, VOTE_MOTION = range(9)
 MASK_NONZERO, MASK_EQ1, MASK_CLASS = 0, 1, 2
 RNG_IDXS, RNG_RAW32, RNG_PHILOX = 0, 1, 2
 STAGE_ALL, STAGE_GATHER, STAGE_VOTE = 0, 1, 2

@@ -1160,6 +1160,32 @@ distribution_kernel(epb_voting_params p, Workspace ws, const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// 9. ransac_motion_voting (ransac_voting_gpu.py:960-981): mean over the foreground of (vector + pixel
+//    coordinate) per keypoint; zeros for an empty mask.  CTA per (image, keypoint), FP64 sums.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+motion_mean_kernel(epb_voting_params p, Workspace ws, float* __restrict__ pts) {
+  const int v = blockIdx.x, b = blockIdx.y;
+  __shared__ double s_red[2 * 8];
+  const int tn = ws.live[b] ? ws.tn[b] : 0;
+  const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
+  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+  double acc[2] = {0, 0};
+  for (int t = threadIdx.x; t < tn; t += 256) {
+    const uint32_t q = __ldg(fp + t);
+    const float2 d = __ldg(dir + t);
+    // float32 "cur_vert + coords" like the reference (:977), accumulated in double
+    acc[0] += (double)__fadd_rn(d.x, (float)(q & 0xffff));
+    acc[1] += (double)__fadd_rn(d.y, (float)(q >> 16));
+  }
+  block_sum_d<2>(acc, s_red);
+  if (threadIdx.x == 0) {
+    float2* out = reinterpret_cast<float2*>(pts) + (size_t)b * p.vn + v;
+    *out = tn > 0 ? make_float2((float)(acc[0] / tn), (float)(acc[1] / tn)) : make_float2(0.f, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // pybind-level primitives (reference tensor layouts)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1256,6 +1282,7 @@ static void voting_kernel_attributes() {
   prefer_max_shared(field_gather_kernel); prefer_max_shared(hypothesis_kernel); prefer_max_shared(vote_items_kernel);
   prefer_max_shared(vote_count_kernel<2>); prefer_max_shared(vote_count_kernel<4>); prefer_max_shared(vote_count_kernel<8>);
   prefer_max_shared(counts_export_kernel); prefer_max_shared(winner_refine_kernel); prefer_max_shared(distribution_kernel);
+  prefer_max_shared(motion_mean_kernel);
   prefer_max_shared(generate_hypothesis_kernel); prefer_max_shared(voting_for_hypothesis_kernel);
   prefer_max_shared(generate_hypothesis_vp_kernel); prefer_max_shared(voting_for_hypothesis_vp_kernel);
   cudaGetLastError();
@@ -1268,7 +1295,7 @@ static bool params_ok(const epb_voting_params* p) {
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->vn <= 0 || p->hn <= 0 || p->rounds <= 0) return false;
   if (p->H > 65535 || p->W > 65535) return false;
   if ((long long)p->H * p->W > 0x7fffffffLL) return false;
-  if (p->mode < EPB_VOTE_V3 || p->mode > EPB_VOTE_V2) return false;
+  if (p->mode < EPB_VOTE_V3 || p->mode > EPB_VOTE_MOTION) return false;
   if (p->classes < 0 || (long long)p->B * (p->classes < 1 ? 1 : p->classes) > 65535) return false;
   if (p->mask_mode < EPB_MASK_NONZERO || p->mask_mode > EPB_MASK_CLASS) return false;
   if (p->rng_mode < EPB_RNG_IDXS || p->rng_mode > EPB_RNG_PHILOX) return false;
@@ -1295,8 +1322,9 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   const epb_voting_params p = virtual_batch(*pp);
   if (p.stage != EPB_STAGE_VOTE && (!io->mask || !io->vertex)) return EPB_ERR_INVALID;
   EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
-  if (p.rng_mode != EPB_RNG_PHILOX && !io->idxs) return EPB_ERR_INVALID;
-  const bool is_layer = p.mode <= EPB_VOTE_V5 || p.mode == EPB_VOTE_V1 || p.mode == EPB_VOTE_V2;
+  if (p.rng_mode != EPB_RNG_PHILOX && !io->idxs && p.mode != EPB_VOTE_MOTION) return EPB_ERR_INVALID;
+  const bool is_layer = p.mode <= EPB_VOTE_V5 || p.mode == EPB_VOTE_V1 || p.mode == EPB_VOTE_V2 ||
+                        p.mode == EPB_VOTE_MOTION;
   const bool is_dist = p.mode == EPB_VOTE_DISTRIBUTION || p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN;
   if (p.stage != EPB_STAGE_GATHER) {   // the gather half produces nothing but the workspace
     if (is_layer && !io->pts) return EPB_ERR_INVALID;
@@ -1391,6 +1419,11 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   if (io->tn_out)
     EPB_RETURN_IF(check_api(cudaMemcpyAsync(io->tn_out, ws.tn, (size_t)p.B * 4, cudaMemcpyDeviceToDevice, s)));
 
+  if (p.mode == EPB_VOTE_MOTION) {   // no hypotheses: the mean of (vector + coordinate) over the foreground
+    ProfScope ps_m(PROF_REFINE, s);
+    motion_mean_kernel<<<dim3(p.vn, p.B), 256, 0, s>>>(p, ws, io->pts);
+    return check_launch();
+  }
   HypCtx hc;
   hc.idxs = io->idxs;
   hc.rng_mode = p.rng_mode;

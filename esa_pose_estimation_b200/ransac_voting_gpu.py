@@ -4,7 +4,7 @@
 Same positional signatures and defaults as the reference:
   ransac_voting_layer (:10)       ransac_voting_layer_v2 (:99)    (multi-class)
   ransac_voting_layer_v3 (:514)   ransac_voting_layer_v4 (:669)   ransac_voting_layer_v5 (:763)
-  ransac_voting_hypothesis (:218) estimate_voting_distribution (:263)
+  ransac_voting_hypothesis (:218) estimate_voting_distribution (:263)   ransac_motion_voting (:960)
   estimate_voting_distribution_with_mean (:333)      vertex_layer_reshape (base_utils.py:311)
 Each call is ONE stream-ordered ``epb_voting_run`` over the whole batch (csrc/voting.cu): no
 per-image Python loop, no ``.item()`` sync, no hn*vn*tn byte tensor.
@@ -91,7 +91,8 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
         raise RuntimeError("vertex must be [b,h,w,vn,2]")
     b, h, w, vn, _ = vertex.shape
     multi = mode in (_lib.VOTE_V1, _lib.VOTE_V2)
-    mask_mode = _lib.MASK_CLASS if multi else (_lib.MASK_NONZERO if mode <= _lib.VOTE_V5 else _lib.MASK_EQ1)
+    mask_mode = _lib.MASK_CLASS if multi else (_lib.MASK_NONZERO if (mode <= _lib.VOTE_V5 or mode == _lib.VOTE_MOTION)
+                                               else _lib.MASK_EQ1)
     mask_u8 = mask.to(torch.uint8).contiguous() if multi else _mask_u8(mask, mask_mode)   # class labels (mask == k+1, :25)
     assert mask_u8.shape == (b, h, w), "mask must be [b,h,w]"
     hn_total = hn * rounds
@@ -150,7 +151,7 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
     if mode_outputs and multi:
         out["pts"] = torch.empty((b, classes, vn, 2), **f32)
         io.pts = _lib.ptr(out["pts"])
-    elif mode_outputs and mode <= _lib.VOTE_V5:
+    elif mode_outputs and (mode <= _lib.VOTE_V5 or mode == _lib.VOTE_MOTION):
         out["pts"] = torch.empty((b, vn, 2), **f32)
         io.pts = _lib.ptr(out["pts"])
         if mode != _lib.VOTE_V3:
@@ -276,6 +277,13 @@ def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256
     o = _run(_lib.VOTE_DISTRIBUTION_WITH_MEAN, mask, vertex, round_hyp_num, rounds, inlier_thresh, min_num,
              max_num, topk=topk, mean_in=mean, **kw)
     return o["mean"], o["cov"]
+
+
+def ransac_motion_voting(mask, vertex):
+    """:960-981: mean over the foreground (mask.byte() != 0) of vertex + pixel coordinate -> [b,vn,2];
+    zeros for an image without foreground."""
+    dummy = torch.zeros((vertex.shape[0], 1, 1, vertex.shape[3], 2), dtype=torch.int32, device=mask.device if mask.is_cuda else None)
+    return _run(_lib.VOTE_MOTION, mask, vertex, 1, 1, 0.999, 1, 2 ** 31 - 1, idxs=dummy)["pts"]
 
 
 def voting_debug(mode, mask, vertex, round_hyp_num, rounds=1, inlier_thresh=0.999, min_num=5, max_num=30000,

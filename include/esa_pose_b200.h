@@ -111,7 +111,9 @@ enum {
   EPB_VOTE_DISTRIBUTION = 4, /* -> mean, cov (top-k) */
   EPB_VOTE_DISTRIBUTION_WITH_MEAN = 5,
   EPB_VOTE_V1 = 6,           /* ransac_voting_layer    (:10)  multi-class, winners -> pts [B,classes,vn,2] */
-  EPB_VOTE_V2 = 7            /* ransac_voting_layer_v2 (:99)  multi-class, pinverse refinement x refine_iters */
+  EPB_VOTE_V2 = 7,           /* ransac_voting_layer_v2 (:99)  multi-class, pinverse refinement x refine_iters */
+  EPB_VOTE_MOTION = 8        /* ransac_motion_voting   (:960) mean of (vector + pixel) over the foreground -> pts;
+                                min_num = 1, max_num = INT_MAX, no random numbers */
 };
 enum {
   EPB_MASK_NONZERO = 0, /* v3/v4/v5: mask.byte() != 0 */

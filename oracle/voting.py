@@ -304,6 +304,20 @@ def ransac_voting_layer_v2(mask, vertex, class_num, round_hyp_num, inlier_thresh
                        idxs_fn or default_idxs_fn(0), selection_fn or default_selection_fn(0), refine_iter_num)
 
 
+def ransac_motion_voting(mask, vertex):
+    """:960-981 -> [b,vn,2]: mean over the foreground of vertex + (x, y); zeros for an empty mask."""
+    b, h, w, vn, _ = vertex.shape
+    out = np.zeros((b, vn, 2), np.float32)
+    for bi in range(b):
+        cur = mask[bi].astype(np.uint8) != 0
+        ys, xs = np.nonzero(cur)
+        if ys.shape[0] < 1:
+            continue
+        coords = np.stack([xs, ys], 1).astype(np.float32)
+        out[bi] = np.mean(vertex[bi][cur] + coords[:, None, :], 0)
+    return out
+
+
 def _distribution_inputs(mask, vertex, round_hyp_num, min_hyp_num, inlier_thresh, min_num, max_num,
                          idxs_fn, selection_fn, degenerate_hn):
     b, h, w, vn, _ = vertex.shape

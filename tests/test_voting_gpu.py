@@ -432,3 +432,17 @@ def test_fused_driver_fuzz_against_oracle(cuda_dev, seed):
     ok = np.isfinite(p4_o).all(axis=-1) & np.isfinite(pts).all(axis=-1)       # singular refinements: NaN on both sides
     assert (np.isfinite(p4_o).all(axis=-1) == np.isfinite(pts).all(axis=-1)).all()
     np.testing.assert_allclose(pts[ok], p4_o[ok], rtol=1e-5, atol=1e-3)
+
+
+def test_motion_voting_matches_oracle(cuda_dev):
+    """ransac_motion_voting (:960-981): foreground mean of vector + coordinate, zeros for an empty mask."""
+    from esa_pose_estimation_b200 import ransac_voting_gpu as rv
+    b, h, w, vn = 3, 40, 56, 4
+    mask, vertex, _ = make_vertex_field(95, b, h, w, vn, 0.3, "randinit")
+    mask[1] = 0
+    mask[2, :, ::2] = 0
+    vx = vertex_hwvn2(vertex)
+    out = rv.ransac_motion_voting(torch.from_numpy(mask).to(cuda_dev), rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev)))
+    ref = ov.ransac_motion_voting(mask, vx)
+    assert (out[1] == 0).all()
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-3)

@@ -20,6 +20,7 @@ VOTE_V3, VOTE_V4, VOTE_V5, VOTE_HYPOTHESIS, VOTE_DISTRIBUTION, VOTE_DISTRIBUTION
 MASK_NONZERO, MASK_EQ1, MASK_CLASS = 0, 1, 2
 RNG_IDXS, RNG_RAW32, RNG_PHILOX = 0, 1, 2
 STAGE_ALL, STAGE_GATHER, STAGE_VOTE = 0, 1, 2
+WEIGHTS_INV_SQRTM, WEIGHTS_INV_MAX_EIG = 0, 1
 POSE_OK, POSE_FAILED, POSE_TOO_FEW = 0, 1, 2
 
 
@@ -66,7 +67,7 @@ SIGNATURES = {
     "epb_rt34_to_rt6": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "epb_pose_pipeline": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "epb_cov_to_weights": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "epb_cov_to_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "epb_esa_score": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -958,13 +958,21 @@ __global__ void rt34_to_rt6_kernel(const double* __restrict__ rt34, int B, doubl
 // weights when cov[0][0] < 1e-6 or any entry is NaN (the reference's guard) -- and, by definition here,
 // when cov is not positive definite (scipy's sqrtm turns complex there and the reference breaks).
 // 2x2 SPD closed form: sqrtm(A) = (A + s I) / t with s = sqrt(det A), t = sqrt(tr A + 2 s).
-__global__ void cov_to_weights_kernel(const float* __restrict__ cov, int n, double* __restrict__ w) {
+__global__ void cov_to_weights_kernel(const float* __restrict__ cov, int n, int mode, double* __restrict__ w) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* c = cov + 4 * (size_t)i;
   const double a = c[0], b01 = c[1], b10 = c[2], d = c[3];
   double* o = w + 3 * (size_t)i;
   o[0] = o[1] = o[2] = 0.0;
+  if (mode == EPB_WEIGHTS_INV_MAX_EIG) {
+    // extend_utils.py:133-141 (uncertainty_pnp_v2): weight = 1 / largest eigenvalue, 0 when cov[0][0] < 1e-5
+    if (c[0] < 1e-5f) return;
+    const double bb = 0.5 * (b01 + b10);
+    const double lmax = 0.5 * (a + d) + sqrt(0.25 * (a - d) * (a - d) + bb * bb);
+    o[0] = o[2] = 1.0 / lmax;
+    return;
+  }
   if (c[0] < 1e-6f || isnan(c[0]) || isnan(c[1]) || isnan(c[2]) || isnan(c[3])) return;
   const double b = 0.5 * (b01 + b10);
   const double det = a * d - b * b;
@@ -1135,11 +1143,11 @@ extern "C" int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* str
   return check_launch();
 }
 
-extern "C" int epb_cov_to_weights(const float* cov, int n, double* w2d, void* stream) {
+extern "C" int epb_cov_to_weights(const float* cov, int n, int mode, double* w2d, void* stream) {
   EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
-  if (!cov || !w2d || n < 0) return EPB_ERR_INVALID;
+  if (!cov || !w2d || n < 0 || mode < EPB_WEIGHTS_INV_SQRTM || mode > EPB_WEIGHTS_INV_MAX_EIG) return EPB_ERR_INVALID;
   if (n == 0) return EPB_OK;
-  cov_to_weights_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cov, n, w2d);
+  cov_to_weights_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cov, n, mode, w2d);
   return check_launch();
 }
 

@@ -127,16 +127,27 @@ def esa_score(pose7_pred, pose7_gt):
     return st_, sr_
 
 
-def cov_to_weights(cov):
-    """evaluation_utils.py:170-181 on the device: cov [...,2,2] f32 -> weights [...,3] f64
-    (wxx,wxy,wyy) = inv(sqrtm(cov)); zeros for degenerate covariances."""
+def cov_to_weights(cov, isotropic=False):
+    """cov [...,2,2] f32 -> LM weights [...,3] f64 (wxx,wxy,wyy) on the device.
+    isotropic=False: inv(sqrtm(cov)) (evaluation_utils.py:170-181);
+    isotropic=True:  1 / largest eigenvalue on the diagonal (uncertainty_pnp_v2, extend_utils.py:133-141)."""
     cov = cov.to(torch.float32).contiguous()
     n = cov.numel() // 4
     w = torch.empty(cov.shape[:-2] + (3,), dtype=torch.float64, device=cov.device)
+    mode = _lib.WEIGHTS_INV_MAX_EIG if isotropic else _lib.WEIGHTS_INV_SQRTM
     with torch.cuda.device(cov.device):
-        _lib.check(_lib.load().epb_cov_to_weights(_lib.ptr(cov), n, _lib.ptr(w), _lib.stream_ptr()),
+        _lib.check(_lib.load().epb_cov_to_weights(_lib.ptr(cov), n, mode, _lib.ptr(w), _lib.stream_ptr()),
                    "epb_cov_to_weights")
     return w
+
+
+def uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix, type='single'):
+    """extend_utils.py:117-178 -> [3,4]: isotropic weights 1 / lambda_max(cov) per keypoint, then the same
+    weighted LM as uncertainty_pnp (initial pose: RANSAC-EPnP on all points instead of cv2's P3P)."""
+    dev = _device()
+    cov = torch.from_numpy(np.ascontiguousarray(np.asarray(covars, np.float32))).to(dev)
+    w = cov_to_weights(cov, isotropic=True).cpu().numpy()
+    return uncertainty_pnp(points_2d, w, points_3d, camera_matrix)
 
 
 def uncertainty_pnp_batch(mean_pts2d, covar, points_3d, K, return_info=False):

@@ -219,10 +219,13 @@ int epb_pose_pack(const double* rt6, int B, float* pose7, double* rt34, void* st
 /* R [B,3,3] (inside rt34 [B,3,4]) -> angle-axis like cv2.Rodrigues; rt6 [B,6]. */
 int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* stream);
 
-/* lib/utils/evaluation_utils.py:170-181 (Evaluator.evaluate_uncertainty): voting covariances
- * cov [n,2,2] f32 -> LM weights w2d [n,3] f64 = (wxx,wxy,wyy) of inv(sqrtm(cov)); zeros where
- * cov[0][0] < 1e-6, an entry is NaN, or cov is not positive definite. */
-int epb_cov_to_weights(const float* cov, int n, double* w2d, void* stream);
+/* Voting covariances cov [n,2,2] f32 -> LM weights w2d [n,3] f64 = (wxx,wxy,wyy).
+ *   EPB_WEIGHTS_INV_SQRTM    lib/utils/evaluation_utils.py:170-181 (Evaluator.evaluate_uncertainty): inv(sqrtm(cov));
+ *                            zeros where cov[0][0] < 1e-6, an entry is NaN, or cov is not positive definite
+ *   EPB_WEIGHTS_INV_MAX_EIG  lib/utils/extend_utils/extend_utils.py:133-141 (uncertainty_pnp_v2): wxx = wyy =
+ *                            1 / largest eigenvalue, wxy = 0; zeros where cov[0][0] < 1e-5 */
+enum { EPB_WEIGHTS_INV_SQRTM = 0, EPB_WEIGHTS_INV_MAX_EIG = 1 };
+int epb_cov_to_weights(const float* cov, int n, int mode, double* w2d, void* stream);
 
 /* val.py:172-228 batched.  preds [B,K,2] f32 crop px, maxvals [B,K] f32, bbox_xy [B,2] f64,
  * rate [B] f64, p3d_model [K,3] f64 (shared) , Kmat [9] f64.

@@ -136,6 +136,16 @@ def cov_to_weights(covar):
     return weights[:, (0, 1, 3)]
 
 
+def isotropic_weights(covars):
+    """extend_utils.py:133-141 (uncertainty_pnp_v2): 1 / max eigenvalue, 0 when cov[0,0] < 1e-5 -> [pn,3]."""
+    covars = np.asarray(covars)
+    w = []
+    for pi in range(covars.shape[0]):
+        w.append(0.0 if covars[pi, 0, 0] < 1e-5 else 1.0 / np.max(np.linalg.eigvals(covars[pi])))
+    w = np.asarray(w, np.float64)[:, None]
+    return np.concatenate([w, np.zeros_like(w), w], 1)
+
+
 def esa_score(q_pred, t_pred, q_gt, t_gt):
     """demo.py:295-310: per-frame ||t^-t||/||t|| + 2 Re(arccos(|q^.q| + 0j))."""
     q_pred, q_gt = np.asarray(q_pred, np.float64), np.asarray(q_gt, np.float64)

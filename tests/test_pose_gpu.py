@@ -237,6 +237,12 @@ def test_cov_to_weights_and_uncertainty_pnp_match_oracle(cuda_dev):
     w = gp.cov_to_weights(torch.from_numpy(cov).to(cuda_dev)).cpu().numpy()
     for i in range(B):
         np.testing.assert_allclose(w[i], opose.cov_to_weights(cov[i]), rtol=2e-4, atol=1e-6)
+    wi = gp.cov_to_weights(torch.from_numpy(cov).to(cuda_dev), isotropic=True).cpu().numpy()   # uncertainty_pnp_v2 weights
+    for i in range(B):
+        np.testing.assert_allclose(wi[i], opose.isotropic_weights(cov[i]), rtol=1e-5, atol=1e-9)
+    r2 = gp.uncertainty_pnp_v2(p2d[0], cov[0], model, ESA_K)
+    ref2 = opose.uncertainty_pnp(p2d[0], opose.isotropic_weights(cov[0]), model, ESA_K)
+    assert _ang(r2[:, :3], ref2[:, :3]) < 1e-3 and np.linalg.norm(r2[:, 3] - ref2[:, 3]) / np.linalg.norm(ref2[:, 3]) < 1e-4
     rt34 = gp.uncertainty_pnp_batch(torch.from_numpy(p2d).to(cuda_dev), torch.from_numpy(cov).to(cuda_dev),
                                     torch.from_numpy(model).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev)).cpu().numpy()
     for i in range(B):

@@ -72,3 +72,10 @@ def test_gather_poses_world2_gloo():
 def test_gather_poses_without_process_group_is_identity():
     x = torch.zeros((3, 7))
     assert pipeline.gather_poses(x, 3) is x
+
+
+def test_camera_constants_match_reference_values():
+    """utils.py:24-39 / base_utils.py:250-252: fx/ppx = 3003.41 px, principal point at the image centre."""
+    from esa_pose_estimation_b200.camera import INTRINSICS, Camera
+    assert abs(Camera.K[0, 0] - 0.0176 / 5.86e-6) < 1e-9 and Camera.K[0, 2] == 960 and Camera.K[1, 2] == 600
+    assert np.allclose(Camera.K, INTRINSICS["esa"], atol=1e-4)

@@ -394,8 +394,8 @@ def run_ours(a):
                    "parallelism": "images sharded by batch, 1 NCCL all_gather of poses" if world > 1 else "single GPU"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes, "clocks": clocks_e2e, "host_numa_binding": numa,
-                "transfer": "mask cudaMemcpyAsync from pinned memory; field read zero-copy from pinned memory by "
-                            "field_gather_kernel (foreground pixels only); poses D2H into pinned memory"},
+                "transfer": "mask cudaMemcpyAsync from pinned memory; field read zero-copy from pinned memory by the "
+                            "compaction kernel (foreground pixel groups only); poses D2H into pinned memory"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "vote_count_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,

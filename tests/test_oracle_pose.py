@@ -119,3 +119,23 @@ def test_cov_to_weights_oracle_matches_closed_form():
         s = np.sqrt(np.linalg.det(c)); t = np.sqrt(np.trace(c) + 2 * s)
         winv = np.linalg.inv((c + s * np.eye(2)) / t)
         np.testing.assert_allclose(w[i], [winv[0, 0], winv[0, 1], winv[1, 1]], rtol=2e-4, atol=1e-6)
+
+
+def test_uncertainty_pnp_oracle_matches_the_reference_python(golden_dir):
+    """oracle/pose.py: uncertainty_pnp / isotropic_weights against tests/golden/uncertainty_pnp.npz = the
+    reference's own extend_utils.uncertainty_pnp / uncertainty_pnp_v2 (imported unmodified, bound to the
+    reference's uncertainty_pnp.cpp; tests/golden/make_golden_uncertainty.py)."""
+    g = np.load(os.path.join(golden_dir, "uncertainty_pnp.npz"))
+    K = g["K"]
+    for i in range(int(g["n_cases"])):
+        p2d, p3d, cov, w = g["p2d_%d" % i], g["p3d_%d" % i], g["cov_%d" % i], g["w_%d" % i]
+        np.testing.assert_allclose(opose.cov_to_weights(cov), w, rtol=1e-12, atol=0)
+        for use_ref in (False, True):
+            if use_ref and olib.ref_pnp_lib(required=False) is None:
+                continue
+            rt = opose.uncertainty_pnp(p2d, w, p3d, K, use_ref=use_ref)
+            assert _ang(rt[:, :3], g["rt_%d" % i][:, :3]) < 1e-5      # arccos near 1: ~1e-6 deg of rounding
+            np.testing.assert_allclose(rt[:, 3], g["rt_%d" % i][:, 3], rtol=1e-8)
+            rt2 = opose.uncertainty_pnp(p2d, opose.isotropic_weights(cov), p3d, K, use_ref=use_ref)
+            assert _ang(rt2[:, :3], g["rt_v2_%d" % i][:, :3]) < 1e-5
+            np.testing.assert_allclose(rt2[:, 3], g["rt_v2_%d" % i][:, 3], rtol=1e-8)

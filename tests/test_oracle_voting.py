@@ -135,3 +135,59 @@ def test_multiclass_oracle_reduces_to_single_class():
     assert v2.shape == (1, 1, 3, 2) and v1.shape == (1, 1, 3, 2)
     np.testing.assert_allclose(v2[:, 0], v3, atol=2e-3)
     assert np.abs(v1[0, 0] - kpts[0]).max() < 3.0
+
+
+# ----------------------------------------------------------------------------- drivers vs the reference's Python
+def test_drivers_match_the_reference_python_drivers():
+    """oracle/voting.py against tests/golden/voting_drivers.npz = outputs of the reference's own
+    ransac_voting_gpu.py (imported unmodified, run on CPU over the C restatement of its kernels;
+    tests/golden/make_golden_voting.py), with the reference's recorded random draws replayed.
+    Hypotheses and inlier counts bit-exact; keypoints within 1e-3 px (float32 cuBLAS/torch sums in
+    the reference, float64 here); variance / confidence / mean / covariance to float32 accuracy."""
+    from tests.golden_voting import Replay, load
+    g = load()
+    mask, vx, hn = g["a_mask"], g["a_vertex"], int(g["a_hn"])
+
+    def rp(name):
+        r = Replay(g, name)
+        return r, dict(idxs_fn=r.idxs_fn, selection_fn=r.selection_fn)
+
+    r, kw = rp("v3")
+    np.testing.assert_allclose(ov.ransac_voting_layer_v3(mask, vx, hn, **kw), g["v3_pts"], atol=1e-3, rtol=0)
+    assert r.exhausted()
+    r, kw = rp("v3sub")
+    np.testing.assert_allclose(ov.ransac_voting_layer_v3(mask, vx, hn, max_num=150, **kw), g["v3sub_pts"], atol=1e-3, rtol=0)
+    assert r.exhausted()
+    r, kw = rp("v3t")
+    np.testing.assert_allclose(ov.ransac_voting_layer_v3(mask, vx, hn, inlier_thresh=0.99, **kw), g["v3t_pts"], atol=1e-3, rtol=0)
+    r, kw = rp("v4")
+    pts, var = ov.ransac_voting_layer_v4(mask, vx, hn, **kw)
+    np.testing.assert_allclose(pts, g["v4_pts"], atol=1e-3, rtol=0)
+    np.testing.assert_allclose(var, g["v4_var"], rtol=2e-3, atol=1e-6)
+    r, kw = rp("v5")
+    pts, conf = ov.ransac_voting_layer_v5(mask, vx, hn, **kw)
+    np.testing.assert_allclose(pts, g["v5_pts"], atol=1e-3, rtol=0)
+    np.testing.assert_array_equal(conf, g["v5_conf"])
+    assert r.exhausted()
+    r, kw = rp("hyp")
+    hyp, counts = ov.ransac_voting_hypothesis(mask, vx, hn, **kw)
+    np.testing.assert_array_equal(hyp.view(np.uint32), g["hyp_hyp"].view(np.uint32))
+    np.testing.assert_array_equal(counts, g["hyp_counts"])
+    r, kw = rp("dist")
+    mean, cov = ov.estimate_voting_distribution(g["d_mask"], g["d_vertex"], round_hyp_num=32, min_hyp_num=96, topk=16, **kw)
+    np.testing.assert_allclose(mean, g["dist_mean"], atol=1e-3, rtol=0)
+    np.testing.assert_allclose(cov, g["dist_cov"], rtol=1e-3, atol=1e-3)
+    assert r.exhausted()
+    r, kw = rp("distm")
+    mean, cov = ov.estimate_voting_distribution_with_mean(g["d_mask"], g["d_vertex"], g["d_kpts"].astype(np.float32),
+                                                          round_hyp_num=32, min_hyp_num=96, **kw)
+    np.testing.assert_array_equal(mean, g["distm_mean"])
+    np.testing.assert_allclose(cov, g["distm_cov"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(ov.ransac_motion_voting(mask, vx), g["motion_pts"], atol=1e-4, rtol=0)
+    lab = g["c_mask"]
+    r, kw = rp("v1")
+    np.testing.assert_array_equal(ov.ransac_voting_layer(lab, vx, 3, hn, **kw), g["v1_pts"])
+    assert r.exhausted()
+    r, kw = rp("v2")
+    np.testing.assert_allclose(ov.ransac_voting_layer_v2(lab, vx, 3, hn, refine_iter_num=2, **kw), g["v2_pts"], atol=1e-3, rtol=0)
+    assert r.exhausted()

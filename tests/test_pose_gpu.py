@@ -249,3 +249,28 @@ def test_cov_to_weights_and_uncertainty_pnp_match_oracle(cuda_dev):
         ref = opose.uncertainty_pnp(p2d[i], w[i], model, ESA_K)
         assert _ang(rt34[i, :, :3], ref[:, :3]) < 1e-3
         assert np.linalg.norm(rt34[i, :, 3] - ref[:, 3]) / np.linalg.norm(ref[:, 3]) < 1e-4
+
+
+def test_uncertainty_pnp_matches_the_reference_python(cuda_dev, golden_dir):
+    """CUDA cov -> weights + weighted LM against tests/golden/uncertainty_pnp.npz = the reference's own
+    extend_utils.uncertainty_pnp / uncertainty_pnp_v2 (unmodified Python over the reference's
+    uncertainty_pnp.cpp; cv2 P3P initialiser there, RANSAC-EPnP here -- same minimiser).
+    Rotation within 1e-3 deg, translation within 1e-4 relative (north_star)."""
+    import os
+    from esa_pose_estimation_b200 import pnp as gp
+    g = np.load(os.path.join(golden_dir, "uncertainty_pnp.npz"))
+    K = g["K"]
+
+    def check(rt, ref):
+        assert _ang(rt[:, :3], ref[:, :3]) < 1e-3
+        assert np.linalg.norm(rt[:, 3] - ref[:, 3]) / np.linalg.norm(ref[:, 3]) < 1e-4
+
+    for i in range(int(g["n_cases"])):
+        p2d, p3d, cov = g["p2d_%d" % i], g["p3d_%d" % i], g["cov_%d" % i]
+        w = gp.cov_to_weights(torch.from_numpy(cov).to(cuda_dev)).cpu().numpy()
+        np.testing.assert_allclose(w, g["w_%d" % i], rtol=2e-4, atol=1e-6)
+        check(gp.uncertainty_pnp(p2d, g["w_%d" % i], p3d, K), g["rt_%d" % i])
+        check(gp.uncertainty_pnp_v2(p2d, cov, p3d, K), g["rt_v2_%d" % i])
+        rt = gp.uncertainty_pnp_batch(torch.from_numpy(p2d[None]).to(cuda_dev), torch.from_numpy(cov[None]).to(cuda_dev),
+                                      torch.from_numpy(p3d).to(cuda_dev), torch.from_numpy(K).to(cuda_dev)).cpu().numpy()[0]
+        check(rt, g["rt_%d" % i])

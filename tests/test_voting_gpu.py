@@ -446,3 +446,60 @@ def test_motion_voting_matches_oracle(cuda_dev):
     ref = ov.ransac_motion_voting(mask, vx)
     assert (out[1] == 0).all()
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-3)
+
+
+def test_drivers_match_the_reference_python_drivers(cuda_dev):
+    """The fused CUDA drivers against tests/golden/voting_drivers.npz: outputs of the reference's own
+    ransac_voting_gpu.py (unmodified, run on CPU over the C restatement of its kernels, see
+    tests/golden/make_golden_voting.py) with the reference's recorded random draws passed in.
+    Hypotheses / inlier counts / v1 winners / confidence bit-exact, keypoints within 1e-3 px."""
+    from esa_pose_estimation_b200 import ransac_voting_gpu as rv
+    from tests.golden_voting import dense_draws, load
+    g = load()
+    hn = int(g["a_hn"])
+    m_t = torch.from_numpy(g["a_mask"]).to(cuda_dev)
+    vert = torch.from_numpy(g["a_vertex"]).to(cuda_dev)
+    live = [True, True, False]                                   # image 2 has 3 foreground pixels < min_num
+
+    def kw(name, live=live, rounds=1):
+        idxs, sel = dense_draws(g, name, live, rounds)
+        d = dict(idxs=torch.from_numpy(idxs).to(cuda_dev))
+        if sel is not None:
+            d["selection"] = torch.from_numpy(sel).to(cuda_dev)
+        return d
+
+    def close(a, ref, atol=1e-3, rtol=0.0):
+        np.testing.assert_allclose(a.cpu().numpy(), ref, rtol=rtol, atol=atol)
+
+    close(rv.ransac_voting_layer_v3(m_t, vert, hn, **kw("v3")), g["v3_pts"])
+    close(rv.ransac_voting_layer_v3(m_t, vert, hn, max_num=150, **kw("v3sub")), g["v3sub_pts"])
+    close(rv.ransac_voting_layer_v3(m_t, vert, hn, inlier_thresh=0.99, **kw("v3t")), g["v3t_pts"])
+    p, var = rv.ransac_voting_layer_v4(m_t, vert, hn, **kw("v4"))
+    close(p, g["v4_pts"])
+    close(var, g["v4_var"], atol=1e-6, rtol=2e-3)
+    p, conf = rv.ransac_voting_layer_v5(m_t, vert, hn, **kw("v5"))
+    close(p, g["v5_pts"])
+    np.testing.assert_array_equal(conf.cpu().numpy(), g["v5_conf"])
+    hyp, cnt = rv.ransac_voting_hypothesis(m_t, vert, hn, **kw("hyp"))
+    np.testing.assert_array_equal(hyp.cpu().numpy().view(np.uint32), g["hyp_hyp"].view(np.uint32))
+    np.testing.assert_array_equal(cnt.cpu().numpy(), g["hyp_counts"])
+    assert cnt.dtype == torch.int64
+    close(rv.ransac_motion_voting(m_t, vert), g["motion_pts"], atol=1e-4)
+    # distributions (own input, tie-free at the k-th ratio)
+    dm, dv = torch.from_numpy(g["d_mask"]).to(cuda_dev), torch.from_numpy(g["d_vertex"]).to(cuda_dev)
+    mean, cov = rv.estimate_voting_distribution(dm, dv, round_hyp_num=32, min_hyp_num=96, topk=16,
+                                                **kw("dist", [True, True], 3))
+    close(mean, g["dist_mean"])
+    close(cov, g["dist_cov"], atol=1e-3, rtol=1e-3)
+    mean_in = torch.from_numpy(g["d_kpts"].astype(np.float32)).to(cuda_dev)
+    mean, cov = rv.estimate_voting_distribution_with_mean(dm, dv, mean_in, round_hyp_num=32, min_hyp_num=96,
+                                                          **kw("distm", [True, True], 3))
+    np.testing.assert_array_equal(mean.cpu().numpy(), g["distm_mean"])
+    close(cov, g["distm_cov"], atol=1e-3, rtol=1e-3)
+    # multi-class: (image, class) pairs in loop order; live = pairs with >= min_num pixels
+    lab = g["c_mask"]
+    live_c = [bool((lab[bi] == k + 1).sum() >= 5) for bi in range(3) for k in range(2)]
+    l_t = torch.from_numpy(lab).to(cuda_dev)
+    p1 = rv.ransac_voting_layer(l_t, vert, 3, hn, **kw("v1", live_c))
+    np.testing.assert_array_equal(p1.cpu().numpy().view(np.uint32), g["v1_pts"].view(np.uint32))
+    close(rv.ransac_voting_layer_v2(l_t, vert, 3, hn, refine_iter_num=2, **kw("v2", live_c)), g["v2_pts"])

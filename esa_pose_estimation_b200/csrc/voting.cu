@@ -1473,7 +1473,11 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     // gather 0.75 -> 0.58 ms per chunk under a concurrent vote, vote 0.68 -> 0.61 ms).
     size_t pad = 0;
     static const int pad_always = [] { const char* e = getenv("EPB_VOTE_HEADROOM_ALWAYS"); return e ? atoi(e) : 0; }();
-    if ((p.stage == EPB_STAGE_VOTE || pad_always) && occ >= 6) {   // (kernels at <= 5 CTAs/SM leave that room anyway)
+    // (only a host-resident field keeps the gather stage busy long enough to matter: it reads over PCIe)
+    cudaPointerAttributes vattr;
+    const bool host_field = io->vertex && cudaPointerGetAttributes(&vattr, io->vertex) == cudaSuccess &&
+                            vattr.type == cudaMemoryTypeHost;
+    if (((p.stage == EPB_STAGE_VOTE && host_field) || pad_always) && occ >= 6) {   // (kernels at <= 5 CTAs/SM leave that room anyway)
       static const int knob = [] { const char* e = getenv("EPB_VOTE_HEADROOM"); return e ? atoi(e) : 2; }();
       const int want = occ - knob;
       const size_t per_sm = 227 * 1024, used = sizeof(VoteSmem) + 1024;

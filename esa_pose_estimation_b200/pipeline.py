@@ -39,22 +39,30 @@ def poses_from_keypoints(kpts, p3d_model, K, bbox_xy=None, rate=None, weights=No
 
 
 def poses_from_vertex(mask, vertex, p3d_model, K, round_hyp_num=512, inlier_thresh=0.999, min_num=5,
-                      max_num=30000, bbox_xy=None, rate=None, chunks=None, **kw):
+                      max_num=30000, bbox_xy=None, rate=None, chunks=None, pipelined=None, **kw):
     """mask [B,H,W], vertex [B,H,W,vn,2] (e.g. vertex_layer_reshape of the NCHW network output).
     -> dict(pose7, rt6, epnp_rt34, status, kpts).
 
     `vertex` (and `mask`) may live in PINNED host memory.  The batch is then cut into `chunks`
     pieces (default 2 when B >= 16; measured 2.29 ms per 64-image call with 2, 2.35 with 1, 2.49 with 3) and flows through three streams: a high-priority stream compacts
     the foreground and reads the field of piece i+1 in place over PCIe while a second stream votes
-    piece i; the caller's stream waits for the keypoints and solves the poses (so the latency-bound
-    pose solve of one call also overlaps the voting of the next).  Results are valid on the caller's
-    stream, as usual."""
+    piece i; a third (high-priority) stream solves the poses once the keypoints are there, so the
+    latency-bound pose solve of one call runs under the voting of the next.  The caller's stream waits
+    for the poses: results are valid on the caller's stream, as usual.
+
+    `pipelined=True` sends DEVICE-resident inputs down the same route (one piece).  Within one caller
+    stream that changes nothing (the inputs of call n+1 are ordered after the results of call n), but
+    calls issued on several caller streams then overlap: each (device, caller stream) pair owns its own
+    workspaces, so several batches can be in flight (bench.py: 2.10 -> 1.9 ms per 64-image call with three).
+    The default for device inputs keeps every kernel on the caller's stream, in ONE shared workspace."""
     host = isinstance(vertex, torch.Tensor) and not vertex.is_cuda
     b = vertex.shape[0]
     if chunks is None:
         chunks = 2 if (host and b >= 16) else 1
     chunks = max(1, min(int(chunks), b))
-    if not host:
+    if pipelined is None:
+        pipelined = host
+    if not host and not pipelined:
         kpts = _voting.ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=inlier_thresh,
                                               min_num=min_num, max_num=max_num, **kw)
         out = poses_from_keypoints(kpts, p3d_model, K, bbox_xy=bbox_xy, rate=rate)
@@ -72,7 +80,8 @@ class _HostPipe:
 
     def __init__(self, dev):
         self.gs = torch.cuda.Stream(device=dev, priority=-1)
-        self.vs = torch.cuda.Stream(device=dev)              # voting; the caller's stream only solves the poses
+        self.vs = torch.cuda.Stream(device=dev)              # voting
+        self.ps = torch.cuda.Stream(device=dev, priority=-1)  # pose solve: its few CTAs go ahead of queued vote CTAs
         self.sets = [None] * self.DEPTH       # each: dict(ws=[tensors], done=[events], need=int)
         self.finished = [None] * self.DEPTH   # event after the pose solve of the call that last used the set
         self.turn = 0
@@ -141,9 +150,9 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
         return d
 
     # device-resident arguments were produced on the current stream; host buffers need no ordering
-    if mask.is_cuda or per_image:
-        ready = torch.cuda.Event()
-        ready.record(cur)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    if mask.is_cuda or vertex.is_cuda or per_image:
         gs.wait_event(ready)
     events, masks_d = [], []
     with torch.cuda.stream(gs):
@@ -174,13 +183,24 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
         voted.record(vs)
     for m_d in masks_d:
         m_d.record_stream(vs)
+    if vertex.is_cuda:                        # device-resident field: read by the gather stream only
+        vertex.record_stream(gs)
+    if mask.is_cuda:
+        mask.record_stream(gs)
     # the pose solve is latency-bound (one warp per image): one launch over the whole batch, on the caller's stream
-    cur.wait_event(voted)
-    kpts.record_stream(cur)
-    out = poses_from_keypoints(kpts, p3d_model, K, bbox_xy=bbox_xy, rate=rate)
+    ps = pipe.ps
+    if ready is not None:
+        ps.wait_event(ready)                  # model / K / bbox / rate of the caller's stream
+    ps.wait_event(voted)
+    with torch.cuda.stream(ps):
+        out = poses_from_keypoints(kpts, p3d_model, K, bbox_xy=bbox_xy, rate=rate)
+        fin = torch.cuda.Event()
+        fin.record(ps)
+    kpts.record_stream(ps)
     out["kpts"] = kpts
-    fin = torch.cuda.Event()
-    fin.record(cur)
+    cur.wait_event(fin)
+    for t in out.values():
+        t.record_stream(cur)
     pipe.finished[turn] = fin
     if philox:
         if sync_rng:                          # exact: what the reference's loop would have consumed

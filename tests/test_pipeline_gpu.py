@@ -84,6 +84,22 @@ def test_host_field_chunked_pipeline_equals_device_run(cuda_dev):
     torch.manual_seed(5)
     ref = pipeline.poses_from_vertex(m_h.to(cuda_dev), rv.vertex_layer_reshape(v_h.to(cuda_dev)), model, K, round_hyp_num=hn)
     off_ref = torch.cuda.default_generators[cuda_dev.index or 0].get_offset()
+    # device-resident inputs through the three-stream route, calls in flight on two caller streams
+    m_d, v_d = m_h.to(cuda_dev), v_h.to(cuda_dev)
+    idxs = torch.randint(0, 1 << 30, (B, 1, hn, vn, 2), dtype=torch.int32, device=cuda_dev)
+    ref_i = pipeline.poses_from_vertex(m_d, rv.vertex_layer_reshape(v_d), model, K, round_hyp_num=hn, idxs=idxs, raw32=True)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda_dev) for _ in range(2)]
+    outs = []
+    for i in range(6):
+        with torch.cuda.stream(streams[i % 2]):
+            outs.append(pipeline.poses_from_vertex(m_d, rv.vertex_layer_reshape(v_d), model, K, round_hyp_num=hn, idxs=idxs,
+                                                   raw32=True, pipelined=True))
+    torch.cuda.synchronize()
+    live = torch.arange(B) != 3
+    for o in outs:
+        assert torch.equal(o["kpts"].view(torch.int32), ref_i["kpts"].view(torch.int32))
+        assert torch.equal(o["pose7"][live].view(torch.int32), ref_i["pose7"][live].view(torch.int32))
     for chunks in (4, 3, 1):
         torch.manual_seed(5)
         out = pipeline.poses_from_vertex(m_h, rv.vertex_layer_reshape(v_h), model, K, round_hyp_num=hn, chunks=chunks)

@@ -79,3 +79,22 @@ def test_camera_constants_match_reference_values():
     from esa_pose_estimation_b200.camera import INTRINSICS, Camera
     assert abs(Camera.K[0, 0] - 0.0176 / 5.86e-6) < 1e-9 and Camera.K[0, 2] == 960 and Camera.K[1, 2] == 600
     assert np.allclose(Camera.K, INTRINSICS["esa"], atol=1e-4)
+
+
+def test_crop_window_matches_the_literal_restatement():
+    """camera.crop_window (vectorised) against data_load_val.py:125-176 restated literally (oracle/decode.py), on boxes
+    that hit every clamp: off the left / top edge, past the right / bottom edge, larger than the frame, square = scale."""
+    from esa_pose_estimation_b200.camera import crop_window
+    from oracle.decode import crop_window as crop_ref
+    rng = np.random.default_rng(3)
+    boxes = []
+    for _ in range(400):
+        cx, cy = rng.uniform(-50, 1970), rng.uniform(-50, 1250)
+        hw, hh = rng.uniform(5, 900), rng.uniform(5, 700)
+        b = [cx - hw, cy - hh, cx + hw, cy + hh]
+        boxes.append([int(v) for v in b] if rng.random() < 0.5 else b)
+    boxes += [[0, 0, 1920, 1200], [-30, -40, 100, 90], [1800, 1100, 2000, 1300], [400, 300, 765, 600], [10, 10, 14, 14]]     # (a box under 2 px divides by zero in the reference)
+    win, size, rate = crop_window(boxes)
+    for i, b in enumerate(boxes):
+        w_ref, s_ref, r_ref = crop_ref(b)
+        assert list(win[i]) == w_ref and int(size[i]) == s_ref and rate[i] == r_ref, (b, win[i], w_ref)

@@ -1370,10 +1370,15 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   }
   // planar field (NCHW network output seen through vertex_layer_reshape): gather fused into the scatter
   const bool planar = p.sx == 1 && p.sy == p.W;   // pixel px of a plane is element px: scalar, line-coalesced reads
-  if (planar) {
-    cudaPointerAttributes attr;
-    const bool host_field = cudaPointerGetAttributes(&attr, io->vertex) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
+  cudaPointerAttributes attr;
+  const bool host_field = cudaPointerGetAttributes(&attr, io->vertex) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  // The fused form exists for host-resident fields (whole 128-byte lines over PCIe).  In HBM the plain pair --
+  // compaction of the coordinates, then one thread per compacted pixel gathering its keypoints -- is faster
+  // (compaction class 0.113 -> 0.082 ms on config[1]): the fused kernel spends its instructions on the 3/4 of the
+  // 32-pixel groups that hold no foreground.  EPB_GATHER_SPLIT=0 forces the fused kernel (profiling).
+  static const int split_knob = [] { const char* e = getenv("EPB_GATHER_SPLIT"); return e ? atoi(e) : 1; }();
+  if (planar && !(split_knob && !host_field)) {
     int dev_id = 0, sm_n = 148;
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&sm_n, cudaDevAttrMultiProcessorCount, dev_id);

@@ -68,6 +68,7 @@ SIGNATURES = {
     "epb_pose_pipeline": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "epb_cov_to_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "epb_p3p": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "epb_esa_score": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

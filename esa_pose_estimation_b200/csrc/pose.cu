@@ -925,6 +925,178 @@ lm_kernel(const double* __restrict__ p2d, const double* __restrict__ p3d, int p3
   }
 }
 
+// ------------------------------------------------------------------------------ P3P (4 points)
+// lib/utils/extend_utils/extend_utils.py:85-95: cv2.solvePnP(flags=SOLVEPNP_P3P) on the four best-weighted
+// correspondences -- the LM initialiser of uncertainty_pnp, and its whole answer when pn == 4.  OpenCV's P3P
+// source is third-party and absent from the reference tree; its contract is: the pose that maps points 0..2
+// onto their image rays exactly and reprojects point 3 best.  Restated from the published problem (Grunert's
+// quartic in the depth ratio v = s3/s1, Haralick et al. 1994, for the candidates; every candidate is then
+// polished by Newton's method on the three inter-point distance equations, which is what makes the result
+// agree with cv2 to 1e-10 px on the three points -- the quartic alone loses 1e-2 px with a 3000 px focal length).
+struct Cplx { double re, im; };
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cplx cdiv(Cplx a, Cplx b) {
+  const double d = b.re * b.re + b.im * b.im;
+  return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+// all four roots of the monic quartic z^4 + c3 z^3 + c2 z^2 + c1 z + c0 (Durand-Kerner)
+__device__ void quartic_roots(double c3, double c2, double c1, double c0, Cplx z[4]) {
+  const double rad = 1.0 + fmax(fmax(fabs(c3), fabs(c2)), fmax(fabs(c1), fabs(c0)));   // Cauchy bound
+  Cplx w = {1.0, 0.0};
+  const Cplx seed = {0.4, 0.9};
+  for (int i = 0; i < 4; ++i) { z[i] = {w.re * rad * 0.5, w.im * rad * 0.5}; w = cmul(w, seed); }
+  for (int it = 0; it < 200; ++it) {
+    double move = 0.0, size = 0.0;
+    for (int i = 0; i < 4; ++i) {
+      Cplx pz = {1.0, 0.0};
+      pz = cmul(pz, z[i]); pz.re += c3;
+      pz = cmul(pz, z[i]); pz.re += c2;
+      pz = cmul(pz, z[i]); pz.re += c1;
+      pz = cmul(pz, z[i]); pz.re += c0;
+      Cplx den = {1.0, 0.0};
+      for (int j = 0; j < 4; ++j) if (j != i) den = cmul(den, csub(z[i], z[j]));
+      const Cplx d = cdiv(pz, den);
+      if (isfinite(d.re) && isfinite(d.im)) { z[i] = csub(z[i], d); move = fmax(move, fabs(d.re) + fabs(d.im)); }
+      size = fmax(size, fabs(z[i].re) + fabs(z[i].im));
+    }
+    if (move <= 1e-15 * fmax(size, 1.0)) break;
+  }
+}
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+// orthonormal frame of three points: e1 along X1 - X0, e3 normal to the triangle; columns of F (row-major 3x3)
+__device__ bool tri_frame(const double X[3][3], double F[9]) {
+  double e1[3], d2[3], e3[3], e2[3];
+  for (int k = 0; k < 3; ++k) { e1[k] = X[1][k] - X[0][k]; d2[k] = X[2][k] - X[0][k]; }
+  const double n1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+  cross3(e1, d2, e3);
+  const double n3 = sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+  if (!(n1 > 0.0) || !(n3 > 0.0)) return false;
+  for (int k = 0; k < 3; ++k) { e1[k] /= n1; e3[k] /= n3; }
+  cross3(e3, e1, e2);
+  for (int k = 0; k < 3; ++k) { F[3 * k] = e1[k]; F[3 * k + 1] = e2[k]; F[3 * k + 2] = e3[k]; }
+  return true;
+}
+// P [4][3] world, uv [4][2] pixels.  Returns false when no candidate has positive depths.
+__device__ bool p3p_solve(const double P[4][3], const double uv[4][2], const Cam& cam, double R[9], double t[3]) {
+  double f[3][3];
+  for (int i = 0; i < 3; ++i) {
+    const double x = (uv[i][0] - cam.uc) / cam.fu, y = (uv[i][1] - cam.vc) / cam.fv;
+    const double n = sqrt(x * x + y * y + 1.0);
+    f[i][0] = x / n; f[i][1] = y / n; f[i][2] = 1.0 / n;
+  }
+  auto d2 = [&](int i, int j) {
+    const double a = P[i][0] - P[j][0], b = P[i][1] - P[j][1], c = P[i][2] - P[j][2];
+    return a * a + b * b + c * c;
+  };
+  auto dotf = [&](int i, int j) { return f[i][0] * f[j][0] + f[i][1] * f[j][1] + f[i][2] * f[j][2]; };
+  const double a2 = d2(1, 2), b2 = d2(0, 2), c2 = d2(0, 1);
+  const double ca = dotf(1, 2), cb = dotf(0, 2), cg = dotf(0, 1);
+  if (!(b2 > 0.0)) return false;
+  const double q = (a2 - c2) / b2, r = (a2 + c2) / b2;
+  const double A4 = (q - 1) * (q - 1) - 4 * c2 / b2 * ca * ca;
+  const double A3 = 4 * (q * (1 - q) * cb - (1 - r) * ca * cg + 2 * c2 / b2 * ca * ca * cb);
+  const double A2 = 2 * (q * q - 1 + 2 * q * q * cb * cb + 2 * (b2 - c2) / b2 * ca * ca - 4 * r * ca * cb * cg +
+                         2 * (b2 - a2) / b2 * cg * cg);
+  const double A1 = 4 * (-q * (1 + q) * cb + 2 * a2 / b2 * cg * cg * cb - (1 - r) * ca * cg);
+  const double A0 = (1 + q) * (1 + q) - 4 * a2 / b2 * cg * cg;
+  Cplx z[4];
+  quartic_roots(A3 / A4, A2 / A4, A1 / A4, A0 / A4, z);
+  double FP[9];
+  if (!tri_frame(P, FP)) return false;
+  double best = INFINITY;
+  bool found = false;
+  for (int k = 0; k < 4; ++k) {
+    const double v = z[k].re;
+    if (!isfinite(v) || !(fabs(z[k].im) <= 1e-4 * fmax(1.0, fabs(v)))) continue;
+    const double den = 2 * (cg - v * ca), s1sq = b2 / (1 + v * v - 2 * v * cb);
+    if (!(s1sq > 0.0) || den == 0.0) continue;
+    const double u = ((q - 1) * v * v - 2 * q * cb * v + 1 + q) / den;
+    double s[3] = {sqrt(s1sq), 0, 0};
+    s[1] = u * s[0]; s[2] = v * s[0];
+    // Newton on  s2^2 + s3^2 - 2 s2 s3 cos(alpha) = a^2,  s1^2 + s3^2 - 2 s1 s3 cos(beta) = b^2,
+    //            s1^2 + s2^2 - 2 s1 s2 cos(gamma) = c^2
+    bool ok = true;
+    for (int it = 0; it < 8 && ok; ++it) {
+      const double g0 = s[1] * s[1] + s[2] * s[2] - 2 * s[1] * s[2] * ca - a2;
+      const double g1 = s[0] * s[0] + s[2] * s[2] - 2 * s[0] * s[2] * cb - b2;
+      const double g2 = s[0] * s[0] + s[1] * s[1] - 2 * s[0] * s[1] * cg - c2;
+      const double J[3][3] = {{0, 2 * s[1] - 2 * s[2] * ca, 2 * s[2] - 2 * s[1] * ca},
+                              {2 * s[0] - 2 * s[2] * cb, 0, 2 * s[2] - 2 * s[0] * cb},
+                              {2 * s[0] - 2 * s[1] * cg, 2 * s[1] - 2 * s[0] * cg, 0}};
+      const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                         J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+      if (!(fabs(det) > 0.0) || !isfinite(det)) { ok = false; break; }
+      const double dx0 = (g0 * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (g1 * J[2][2] - J[1][2] * g2) +
+                          J[0][2] * (g1 * J[2][1] - J[1][1] * g2)) / det;
+      const double dx1 = (J[0][0] * (g1 * J[2][2] - J[1][2] * g2) - g0 * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                          J[0][2] * (J[1][0] * g2 - g1 * J[2][0])) / det;
+      const double dx2 = (J[0][0] * (J[1][1] * g2 - g1 * J[2][1]) - J[0][1] * (J[1][0] * g2 - g1 * J[2][0]) +
+                          g0 * (J[1][0] * J[2][1] - J[1][1] * J[2][0])) / det;
+      s[0] -= dx0; s[1] -= dx1; s[2] -= dx2;
+    }
+    if (!ok || !(s[0] > 0.0) || !(s[1] > 0.0) || !(s[2] > 0.0)) continue;
+    double Q[3][3], FQ[9], Rc[9], tc[3];
+    for (int i = 0; i < 3; ++i) for (int d = 0; d < 3; ++d) Q[i][d] = s[i] * f[i][d];
+    if (!tri_frame(Q, FQ)) continue;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Rc[3 * i + j] = FQ[3 * i] * FP[3 * j] + FQ[3 * i + 1] * FP[3 * j + 1] + FQ[3 * i + 2] * FP[3 * j + 2];
+    for (int i = 0; i < 3; ++i) tc[i] = Q[0][i] - (Rc[3 * i] * P[0][0] + Rc[3 * i + 1] * P[0][1] + Rc[3 * i + 2] * P[0][2]);
+    const double xc = Rc[0] * P[3][0] + Rc[1] * P[3][1] + Rc[2] * P[3][2] + tc[0];
+    const double yc = Rc[3] * P[3][0] + Rc[4] * P[3][1] + Rc[5] * P[3][2] + tc[1];
+    const double zc = Rc[6] * P[3][0] + Rc[7] * P[3][1] + Rc[8] * P[3][2] + tc[2];
+    const double du = cam.uc + cam.fu * xc / zc - uv[3][0], dv = cam.vc + cam.fv * yc / zc - uv[3][1];
+    const double e = du * du + dv * dv;
+    if (e < best) {
+      best = e; found = true;
+      for (int i = 0; i < 9; ++i) R[i] = Rc[i];
+      for (int i = 0; i < 3; ++i) t[i] = tc[i];
+    }
+  }
+  return found;
+}
+
+// One thread per problem.  w2d == nullptr: n must be 4 and the points are used in the given order.  Otherwise
+// the four correspondences with the largest wxx + wxy are taken in ascending order of that key
+// (extend_utils.py:83: np.argsort(weights_2d[:,0] + weights_2d[:,1])[-4:]; ties: lower index first).
+__global__ void p3p_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __restrict__ p2d,
+                           const double* __restrict__ w2d, const double* __restrict__ K, int K_batched, int B, int n,
+                           double* __restrict__ rt34, int32_t* __restrict__ status) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= B) return;
+  int sel[4] = {0, 1, 2, 3};
+  if (w2d) {
+    // selection sort of the four largest keys, then ascending order (stable argsort semantics)
+    unsigned taken = 0;
+    for (int r = 3; r >= 0; --r) {
+      int bi = -1; double bk = 0;
+      for (int i = 0; i < n; ++i) {
+        if ((taken >> i) & 1u) continue;
+        const double key = w2d[((size_t)img * n + i) * 3] + w2d[((size_t)img * n + i) * 3 + 1];
+        if (bi < 0 || key > bk || (key == bk && i > bi)) { bi = i; bk = key; }
+      }
+      sel[r] = bi; taken |= 1u << bi;
+    }
+  }
+  double P[4][3], uv[4][2];
+  for (int k = 0; k < 4; ++k) {
+    const double* q3 = p3d + ((p3d_batched ? (size_t)img * n : 0) + sel[k]) * 3;
+    const double* q2 = p2d + ((size_t)img * n + sel[k]) * 2;
+    P[k][0] = q3[0]; P[k][1] = q3[1]; P[k][2] = q3[2]; uv[k][0] = q2[0]; uv[k][1] = q2[1];
+  }
+  const Cam cam = load_cam(K, K_batched, img);
+  double R[9], t[3];
+  const bool ok = p3p_solve(P, uv, cam, R, t);
+  double* o = rt34 + (size_t)img * 12;
+  for (int i = 0; i < 3; ++i) {
+    o[4 * i] = ok ? R[3 * i] : NAN; o[4 * i + 1] = ok ? R[3 * i + 1] : NAN; o[4 * i + 2] = ok ? R[3 * i + 2] : NAN;
+    o[4 * i + 3] = ok ? t[i] : NAN;
+  }
+  if (status) status[img] = ok ? EPB_POSE_OK : EPB_POSE_FAILED;
+}
+
 __global__ void pose_pack_kernel(const double* __restrict__ rt6, int B, float* __restrict__ pose7,
                                  double* __restrict__ rt34) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1140,6 +1312,15 @@ extern "C" int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* str
   if (!rt34 || !rt6 || B < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   rt34_to_rt6_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rt34, B, rt6);
+  return check_launch();
+}
+
+extern "C" int epb_p3p(const double* p3d, int p3d_batched, const double* p2d, const double* w2d, const double* K,
+                       int K_batched, int B, int n, double* rt34, int32_t* status, void* stream) {
+  EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
+  if (!p3d || !p2d || !K || !rt34 || B < 0 || n < 4 || n > 32 || (!w2d && n != 4)) return EPB_ERR_INVALID;
+  if (B == 0) return EPB_OK;
+  p3p_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p3d, p3d_batched, p2d, w2d, K, K_batched, B, n, rt34, status);
   return check_launch();
 }
 

@@ -141,26 +141,47 @@ def cov_to_weights(cov, isotropic=False):
     return w
 
 
+def p3p_batch(p3d, p2d, K, w2d=None, return_status=False):
+    """cv2.solvePnP(flags=SOLVEPNP_P3P) on four correspondences, batched on the device (extend_utils.py:85-89).
+    p3d [n,3] | [B,n,3], p2d [B,n,2], K [3,3] | [B,3,3].  w2d None: n == 4, points in the given order (0..2 are met
+    exactly, 3 picks the root).  w2d [B,n,3]: the four with the largest wxx + wxy, ascending
+    (np.argsort(w[:,0] + w[:,1])[-4:], extend_utils.py:83).  -> rt34 [B,3,4] f64 (NaN where P3P has no root)."""
+    dev = p2d.device
+    p2d, p3d, K = _f64(p2d, dev), _f64(p3d, dev), _f64(K, dev)
+    b, n = p2d.shape[0], p2d.shape[1]
+    w = None if w2d is None else _f64(w2d, dev)
+    rt34 = torch.empty((b, 3, 4), dtype=torch.float64, device=dev)
+    status = torch.zeros((b,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().epb_p3p(_lib.ptr(p3d), int(p3d.dim() == 3), _lib.ptr(p2d), _lib.ptr(w) if w is not None else None,
+                                       _lib.ptr(K), int(K.dim() == 3), b, n, _lib.ptr(rt34), _lib.ptr(status),
+                                       _lib.stream_ptr()), "epb_p3p")
+    return (rt34, status) if return_status else rt34
+
+
 def uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix, type='single'):
     """extend_utils.py:117-178 -> [3,4]: isotropic weights 1 / lambda_max(cov) per keypoint, then the same
-    weighted LM as uncertainty_pnp (initial pose: RANSAC-EPnP on all points instead of cv2's P3P)."""
+    P3P-initialised weighted LM as uncertainty_pnp."""
     dev = _device()
     cov = torch.from_numpy(np.ascontiguousarray(np.asarray(covars, np.float32))).to(dev)
     w = cov_to_weights(cov, isotropic=True).cpu().numpy()
     return uncertainty_pnp(points_2d, w, points_3d, camera_matrix)
 
 
-def uncertainty_pnp_batch(mean_pts2d, covar, points_3d, K, return_info=False):
+def uncertainty_pnp_batch(mean_pts2d, covar, points_3d, K, return_info=False, init="p3p"):
     """Evaluator.evaluate_uncertainty (evaluation_utils.py:165-188) batched and device-resident:
     mean_pts2d [B,n,2], covar [B,n,2,2] (estimate_voting_distribution output), points_3d [n,3] | [B,n,3],
-    K [3,3] | [B,3,3] -> rt34 [B,3,4] f64.  The reference initialises the LM with cv2's P3P on the four
-    best-weighted points (extend_utils.py:85-89, third-party); here RANSAC-EPnP on all points gives the
-    initial pose -- both lie in the basin of the same weighted-reprojection minimiser."""
+    K [3,3] | [B,3,3] -> rt34 [B,3,4] f64.  As in the reference the LM starts from P3P on the four
+    best-weighted points (extend_utils.py:83-89); `init="epnp"` starts from RANSAC-EPnP on all points instead
+    (both lie in the basin of the same weighted-reprojection minimiser on well-posed input)."""
     dev = mean_pts2d.device
     w = cov_to_weights(covar)
     p2, p3, Kd = _f64(mean_pts2d, dev), _f64(points_3d, dev), _f64(K, dev)
-    init = rt34_to_rt6(pnp_batch(p3, p2, Kd))
-    res = lm_refine_batch(p2, p3, w, Kd, init, return_info=return_info)
+    start = p3p_batch(p3, p2, Kd, w2d=w) if init == "p3p" else pnp_batch(p3, p2, Kd)
+    if p2.shape[1] == 4 and init == "p3p" and not return_info:
+        return start                          # extend_utils.py:91-95: "no other points", the P3P pose is the answer
+    init_rt = rt34_to_rt6(start)
+    res = lm_refine_batch(p2, p3, w, Kd, init_rt, return_info=return_info)
     rt6 = res[0] if return_info else res
     _, rt34 = pose_pack(rt6)
     return (rt34, rt6) + tuple(res[1:]) if return_info else rt34
@@ -205,20 +226,19 @@ def cpnp_m(p3d, p2d, maxvals, K, camera):
 
 
 def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix, init_rt=None):
-    """extend_utils.py:64-115 -> [3,4].  The reference initialises with cv2's P3P on the four
-    best-weighted points; here the initial pose is RANSAC-EPnP on all points unless `init_rt`
-    ([6] angle-axis, t) is given.  Both converge to the same LM minimiser on well-posed input."""
+    """extend_utils.py:64-115 -> [3,4]: P3P on the four correspondences with the largest wxx + wxy
+    (np.argsort(...)[-4:], :83-89) gives the initial pose -- and the answer itself when pn == 4 (:91-95) --
+    then the weighted LM of uncertainty_pnp.cpp.  `init_rt` ([6] angle-axis, t) overrides the P3P start."""
     pn = points_2d.shape[0]
     assert points_3d.shape[0] == pn and pn >= 4
-    if pn == 4 and init_rt is None:
-        # extend_utils.py:91-95 returns cv2's P3P pose itself for exactly four points; that third-party
-        # solver is not restated here and EPnP-RANSAC needs five: refuse rather than return garbage
-        raise NotImplementedError("uncertainty_pnp with exactly 4 points needs init_rt (cv2 P3P is not restated)")
     dev = _device()
     p2, p3, w = _f64(points_2d, dev)[None], _f64(points_3d, dev)[None], _f64(weights_2d, dev)[None]
     K = _f64(camera_matrix, dev)
     if init_rt is None:
-        init = rt34_to_rt6(pnp_batch(p3, p2, K))
+        rt34 = p3p_batch(p3, p2, K, w2d=w)
+        if pn == 4:
+            return rt34[0].cpu().numpy()
+        init = rt34_to_rt6(rt34)
     else:
         init = _f64(init_rt, dev).reshape(1, 6)
     rt6 = lm_refine_batch(p2, p3, w, K, init)

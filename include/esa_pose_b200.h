@@ -28,6 +28,8 @@
  *                                    EPnP-RANSAC, LM, quaternion)
  *   epb_esa_score                    demo.py:295-310
  *   epb_cov_to_weights               lib/utils/evaluation_utils.py:170-181 cov -> inv(sqrtm(cov)) weights
+ *   epb_p3p                          lib/utils/extend_utils/extend_utils.py:83-95 (and :147-156): cv2.solvePnP(P3P)
+ *                                    on the four best-weighted correspondences
  */
 #ifndef ESA_POSE_B200_H_
 #define ESA_POSE_B200_H_
@@ -226,6 +228,16 @@ int epb_rt34_to_rt6(const double* rt34, int B, double* rt6, void* stream);
  *                            1 / largest eigenvalue, wxy = 0; zeros where cov[0][0] < 1e-5 */
 enum { EPB_WEIGHTS_INV_SQRTM = 0, EPB_WEIGHTS_INV_MAX_EIG = 1 };
 int epb_cov_to_weights(const float* cov, int n, int mode, double* w2d, void* stream);
+
+/* extend_utils.py:83-95: the pose through three correspondences that reprojects a fourth best
+ * (cv2.solvePnP(flags=SOLVEPNP_P3P) on 4 points) -- uncertainty_pnp's LM initialiser, and its whole answer
+ * when pn == 4.  p3d [n,3] (or [B,n,3] if p3d_batched), p2d [B,n,2], K [9] (or [B,9]), all f64.
+ * w2d == NULL: n must be 4, points used in the given order (0..2 exact, 3 disambiguates).
+ * w2d [B,n,3]: the four correspondences with the largest wxx + wxy, in ascending order of that key
+ * (np.argsort(w[:,0] + w[:,1])[-4:]).  -> rt34 [B,3,4] f64 (NaN + EPB_POSE_FAILED in status when no
+ * candidate has positive depths). */
+int epb_p3p(const double* p3d, int p3d_batched, const double* p2d, const double* w2d, const double* K,
+            int K_batched, int B, int n, double* rt34, int32_t* status, void* stream);
 
 /* val.py:172-228 batched.  preds [B,K,2] f32 crop px, maxvals [B,K] f32, bbox_xy [B,2] f64,
  * rate [B] f64, p3d_model [K,3] f64 (shared) , Kmat [9] f64.

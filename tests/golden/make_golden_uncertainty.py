@@ -38,7 +38,8 @@ ref_ext.lib = ffi.dlopen(os.path.join(ROOT, "oracle", "_ref", "libuncertainty_pn
 
 def main():
     out = {"K": ESA_K}
-    cases = [(400, 11, 0.6), (401, 11, 1.0), (402, 8, 0.4), (403, 30, 0.8), (404, 11, 0.2), (405, 16, 0.7)]
+    cases = [(400, 11, 0.6), (401, 11, 1.0), (402, 8, 0.4), (403, 30, 0.8), (404, 11, 0.2), (405, 16, 0.7),
+             (406, 4, 0.5), (407, 4, 0.3), (408, 5, 0.4)]          # pn == 4: the P3P pose itself (:91-95)
     for i, (seed, n, noise) in enumerate(cases):
         c = make_pose_case(seed, n, noise, 0)
         rng = np.random.default_rng(seed)

@@ -274,3 +274,37 @@ def test_uncertainty_pnp_matches_the_reference_python(cuda_dev, golden_dir):
         rt = gp.uncertainty_pnp_batch(torch.from_numpy(p2d[None]).to(cuda_dev), torch.from_numpy(cov[None]).to(cuda_dev),
                                       torch.from_numpy(p3d).to(cuda_dev), torch.from_numpy(K).to(cuda_dev)).cpu().numpy()[0]
         check(rt, g["rt_%d" % i])
+
+
+def test_p3p_matches_cv2(cuda_dev):
+    """epb_p3p against cv2.solvePnP(flags=SOLVEPNP_P3P) called the way extend_utils.py:85-89 calls it (third party,
+    4.13.0 here): 4 noisy correspondences, rotation within 1e-3 deg, translation within 1e-4 relative; and the
+    best-four selection by weight equals np.argsort(wxx + wxy)[-4:]."""
+    import cv2
+    from esa_pose_estimation_b200 import pnp as gp
+    n_cases = 200
+    p3 = np.zeros((n_cases, 4, 3)); p2 = np.zeros((n_cases, 4, 2)); ref = np.zeros((n_cases, 3, 4))
+    for i in range(n_cases):
+        c = make_pose_case(7000 + i, 4, 0.5, 0)
+        p3[i], p2[i] = c["p3d"], c["p2d"]
+        ok, rv, tv = cv2.solvePnP(np.expand_dims(p3[i], 0), np.expand_dims(p2[i], 0), ESA_K, np.zeros((8, 1)), None, None, False,
+                                  flags=cv2.SOLVEPNP_P3P)
+        assert ok
+        ref[i] = np.concatenate([cv2.Rodrigues(rv)[0], tv], -1)
+    out, st = gp.p3p_batch(torch.from_numpy(p3).to(cuda_dev), torch.from_numpy(p2).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev),
+                           return_status=True)
+    out = out.cpu().numpy()
+    assert (st.cpu().numpy() == 0).all()
+    for i in range(n_cases):
+        assert _ang(out[i, :, :3], ref[i, :, :3]) < 1e-3, i
+        assert np.linalg.norm(out[i, :, 3] - ref[i, :, 3]) / np.linalg.norm(ref[i, :, 3]) < 1e-4, i
+    # selection of the four best-weighted correspondences among n = 9
+    rng = np.random.default_rng(4)
+    c = make_pose_case(7300, 9, 0.4, 0)
+    w = np.stack([rng.uniform(0.1, 2, 9), rng.uniform(-0.2, 0.2, 9), rng.uniform(0.1, 2, 9)], 1)
+    idxs = np.argsort(w[:, 0] + w[:, 1])[-4:]
+    a = gp.p3p_batch(torch.from_numpy(c["p3d"]).to(cuda_dev), torch.from_numpy(c["p2d"][None]).to(cuda_dev),
+                     torch.from_numpy(ESA_K).to(cuda_dev), w2d=torch.from_numpy(w[None]).to(cuda_dev)).cpu().numpy()[0]
+    b = gp.p3p_batch(torch.from_numpy(c["p3d"][idxs]).to(cuda_dev), torch.from_numpy(c["p2d"][idxs][None]).to(cuda_dev),
+                     torch.from_numpy(ESA_K).to(cuda_dev)).cpu().numpy()[0]
+    np.testing.assert_array_equal(a, b)

@@ -123,3 +123,24 @@ def test_host_pipeline_with_many_hypotheses(cuda_dev):
     torch.manual_seed(9)
     out = pipeline.poses_from_vertex(m_h, rv.vertex_layer_reshape(v_h), model, K, round_hyp_num=hn, chunks=4)
     assert torch.equal(out["kpts"].view(torch.int32), ref.view(torch.int32))
+
+
+def test_heatmap_path_replays_as_a_cuda_graph(cuda_dev):
+    """The heatmap chain (decode, refine, pose) neither synchronises nor allocates inside the C library, so it can
+    be captured once and replayed: the replay is bit-identical to the eager call, also after the inputs change."""
+    from esa_pose_estimation_b200 import pipeline
+    B, kp, S = 3, 11, 64
+    model = torch.from_numpy(tango_model(kp, seed=9)).to(cuda_dev)
+    K = torch.from_numpy(np.array([[120.0, 0, 32], [0, 120.0, 32], [0, 0, 1]])).to(cuda_dev)
+    g = pipeline.GraphedHeatmapPose(B, kp, S, S, model, K, cuda_dev, min_k=8)
+    for seed in (5, 6):
+        hm, _ = make_heatmaps(seed, B, kp, S, S, "gauss")
+        hm_t = torch.from_numpy(hm).to(cuda_dev)
+        bbox = torch.zeros((B, 2), dtype=torch.float64, device=cuda_dev)
+        rate = torch.ones((B,), dtype=torch.float64, device=cuda_dev)
+        eager = pipeline.poses_from_heatmaps(hm_t, bbox, rate, model, K, min_k=8)
+        out = g(hm_t, bbox, rate)
+        torch.cuda.synchronize()
+        for k in ("pose7", "rt6", "xy", "maxval"):
+            a, b = out[k], eager[k]
+            assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), k

@@ -81,8 +81,20 @@ def c1():
         k = i[0] % 8; i[0] += 1
         return pipeline.poses_from_heatmaps(hm[k:k + 1], bbox[k:k + 1], rate[k:k + 1], model, K, min_k=8)
     ms = timed(step, 50)
+    # the same call captured once as a CUDA graph and replayed on static buffers (pipeline.GraphedHeatmapPose)
+    g = pipeline.GraphedHeatmapPose(1, 11, 128, 128, model, K, DEV, min_k=8)
+    eager = pipeline.poses_from_heatmaps(hm[:1], bbox[:1], rate[:1], model, K, min_k=8)["pose7"].clone()
+    assert torch.equal(g(hm[:1], bbox[:1], rate[:1])["pose7"], eager)
+    ms_graph = timed(lambda: g(None, None, None, copy_inputs=False), 50)
+    j = [0]
+
+    def step_graph_copy():
+        k = j[0] % 8; j[0] += 1
+        return g(hm[k:k + 1], bbox[k:k + 1], rate[k:k + 1])
+    ms_graph_copy = timed(step_graph_copy, 50)
     return {"config": "C1 single frame 11x128x128 heatmaps -> decode + EPnP-RANSAC + LM (device resident, no sync inside)",
             "metric": "latency per frame", "value": ms * 1e3, "unit": "us", "higher_is_better": False,
+            "cuda_graph_replay_us": ms_graph * 1e3, "cuda_graph_replay_with_input_copies_us": ms_graph_copy * 1e3,
             "note": "reference val.py path on the CPU: ~0.8 ms decode + 0.5 ms cv2 EPnP + LM per frame (SURVEY 8d)"}
 
 

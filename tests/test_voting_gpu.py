@@ -241,11 +241,13 @@ def test_full_size_properties(cuda_dev):
     assert cnt.min() >= 0 and (cnt.max(axis=(1, 2)) <= tn).all()
     pts = dbg["pts"].cpu().numpy()
     assert np.abs(pts - kpts).max() < 1.5                               # recovers the planted keypoints (2 deg noise)
-    # one image checked exactly against the oracle using the counts' own hypotheses
-    vx0 = vertex_hwvn2(vertex[:1])
-    _, coords, direct = ov.compact(mask[0] != 0, vx0[0], 30000, ov.default_selection_fn(0), 0)
-    hyp0 = dbg["hyp"][0].cpu().numpy()
-    np.testing.assert_array_equal(ov.vote_counts(direct, coords, hyp0[:64], 0.999), cnt[0, :64])
+    # five images checked exactly against the oracle, every one of their 512 x 11 counts (92 M pair tests each),
+    # using the counts' own hypotheses (drawn by the in-kernel Philox stream)
+    for bi in (0, 1, 18, 35, 63):
+        vxb = vertex_hwvn2(vertex[bi:bi + 1])
+        _, coords, direct = ov.compact(mask[bi] != 0, vxb[0], 30000, ov.default_selection_fn(0), 0)
+        hyp_b = dbg["hyp"][bi].cpu().numpy()
+        np.testing.assert_array_equal(ov.vote_counts(direct, coords, hyp_b, 0.999), cnt[bi])
     # same seed -> identical result (determinism, no atomics races in the count)
     torch.manual_seed(7)
     dbg2 = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn)

@@ -505,3 +505,28 @@ def test_drivers_match_the_reference_python_drivers(cuda_dev):
     p1 = rv.ransac_voting_layer(l_t, vert, 3, hn, **kw("v1", live_c))
     np.testing.assert_array_equal(p1.cpu().numpy().view(np.uint32), g["v1_pts"].view(np.uint32))
     close(rv.ransac_voting_layer_v2(l_t, vert, 3, hn, refine_iter_num=2, **kw("v2", live_c)), g["v2_pts"])
+
+
+def test_config4_size_distribution_matches_oracle(cuda_dev):
+    """BASELINE config[3] size for one image: 768x768 field, 11 keypoints, 8 rounds x 256 = 2048 hypotheses, foreground
+    147 k pixels subsampled to ~30000 (max_num), top-128 mean / covariance.  676 M pair tests through the C restatement:
+    hypotheses and counts bit-exact, mean within 1e-3 px, covariance to float32 accuracy."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    h = w = 768
+    vn, hn, rounds = 11, 256, 8
+    mask, vertex, _ = make_vertex_field(91, 1, h, w, vn, 0.25, noise_deg=2.0)
+    vx = vertex_hwvn2(vertex)
+    idxs, selection, fn, sel = _idxs_for(mask, vx, hn, rounds, 30000, 21, eq1=True)
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev))
+    kw = dict(idxs=torch.from_numpy(idxs).to(cuda_dev), selection=torch.from_numpy(selection).to(cuda_dev))
+    dbg = rv.voting_debug(_lib.VOTE_DISTRIBUTION, m_t, vert, hn, rounds=rounds, inlier_thresh=0.99, topk=128, **kw)
+    _, coords, direct = ov.compact(mask[0] == 1, vx[0], 30000, sel, 0)
+    assert int(dbg["tn"][0]) == coords.shape[0] and 25000 < coords.shape[0] < 35000
+    hyp = dbg["hyp"][0].cpu().numpy()                                      # [rounds*hn, vn, 2]
+    hyp_o = np.concatenate([ov.generate_hypothesis(direct, coords, idxs[0, r]) for r in range(rounds)], 0)
+    np.testing.assert_array_equal(hyp.view(np.int32), hyp_o.view(np.int32))
+    np.testing.assert_array_equal(dbg["counts"][0].cpu().numpy(), ov.vote_counts(direct, coords, hyp_o, 0.99))
+    mean_o, cov_o = ov.estimate_voting_distribution(mask, vx, hn, hn * rounds, 128, idxs_fn=fn, selection_fn=sel)
+    np.testing.assert_allclose(dbg["mean"].cpu().numpy(), mean_o, rtol=0, atol=1e-3)
+    np.testing.assert_allclose(dbg["cov"].cpu().numpy(), cov_o, rtol=1e-3, atol=1e-3)

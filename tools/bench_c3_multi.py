@@ -4,7 +4,8 @@ sharded by frame across the GPUs of one box, one NCCL all_gather of the [3000, 7
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 \\
         tools/bench_c3_multi.py
-Each rank holds its 375 frames (2.4 GB of heatmaps) in HBM and runs them as calls of 125 frames (decode ->
+Each rank holds its 375 frames (2.4 GB of heatmaps) in HBM and runs them as calls of EPB_C3_PER_CALL frames (default:
+all 375 in one call -- the pose solve is latency-bound, so one call of 375 costs little more than one of 125; decode ->
 select / un-crop -> EPnP-RANSAC -> LM), then the poses are gathered; timed with CUDA events between barriers,
 maximum over the ranks; rank 0 prints one JSON line.  One pass = the whole 3000-frame set."""
 import json
@@ -29,7 +30,7 @@ def main():
     bc.DEV = dev
     from esa_pose_estimation_b200 import pipeline
     from tests.synth import ESA_K
-    total, per_call = 3000, 125
+    total, per_call = 3000, int(os.environ.get("EPB_C3_PER_CALL", "375"))
     s, e = pipeline.shard_range(total, rank, world)
     n = e - s
     hm, bbox, rate, model = bc.heatmap_batch(n, 11, 384, 100 + rank)

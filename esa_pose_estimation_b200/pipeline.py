@@ -12,13 +12,52 @@ import torch
 from . import inference, pnp as _pnp, ransac_voting_gpu as _voting
 
 
-def poses_from_heatmaps(hms, bbox_xy, rate, p3d_model, K, min_k=24, sel_thresh=0.8, weighted=True):
+_pose_streams = {}
+
+
+def poses_from_heatmaps(hms, bbox_xy, rate, p3d_model, K, min_k=24, sel_thresh=0.8, weighted=True, chunk_frames=384):
     """hms [B,Kp,H,W] CUDA f32; bbox_xy [B,2]; rate [B]; p3d_model [Kp,3]; K [3,3].
-    -> dict(pose7 [B,7] f32 (qw,qx,qy,qz,tx,ty,tz), rt6, epnp_rt34, status, xy, maxval)."""
-    xy, maxval, _ = inference.decode_heatmaps(hms, refine=True)
-    out = _pnp.pose_pipeline(xy, maxval, bbox_xy, rate, p3d_model, K, min_k=min_k, sel_thresh=sel_thresh,
-                             weighted=weighted)
-    out["xy"], out["maxval"] = xy, maxval
+    -> dict(pose7 [B,7] f32 (qw,qx,qy,qz,tx,ty,tz), rt6, epnp_rt34, status, xy, maxval).
+
+    Sets of more than `chunk_frames` frames go through in pieces: the decode of piece i+1 (HBM-bound, the caller's
+    stream) runs while a second, high-priority stream solves the poses of piece i (latency-bound, a few small CTAs
+    per SM), so a long set costs little more than reading its heatmaps once.  Results are valid on the caller's
+    stream and identical to the one-piece call."""
+    b = hms.shape[0]
+    if b <= chunk_frames or not hms.is_cuda or torch.cuda.is_current_stream_capturing():
+        xy, maxval, _ = inference.decode_heatmaps(hms, refine=True)
+        out = _pnp.pose_pipeline(xy, maxval, bbox_xy, rate, p3d_model, K, min_k=min_k, sel_thresh=sel_thresh,
+                                 weighted=weighted)
+        out["xy"], out["maxval"] = xy, maxval
+        return out
+    dev = hms.device
+    cur = torch.cuda.current_stream(dev)
+    ps = _pose_streams.get((dev.index, cur.cuda_stream))
+    if ps is None:
+        ps = _pose_streams[(dev.index, cur.cuda_stream)] = torch.cuda.Stream(device=dev, priority=-1)
+    ready = torch.cuda.Event()
+    ready.record(cur)                        # bbox / rate / model / K of the caller's stream
+    ps.wait_event(ready)
+    parts = []
+    for s in range(0, b, chunk_frames):
+        e = min(b, s + chunk_frames)
+        xy, maxval, _ = inference.decode_heatmaps(hms[s:e], refine=True)
+        decoded = torch.cuda.Event()
+        decoded.record(cur)
+        ps.wait_event(decoded)
+        with torch.cuda.stream(ps):
+            o = _pnp.pose_pipeline(xy, maxval, bbox_xy[s:e], rate[s:e], p3d_model, K, min_k=min_k, sel_thresh=sel_thresh,
+                                   weighted=weighted)
+        xy.record_stream(ps); maxval.record_stream(ps)
+        o["xy"], o["maxval"] = xy, maxval
+        parts.append(o)
+    with torch.cuda.stream(ps):
+        out = {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+        done = torch.cuda.Event()
+        done.record(ps)
+    cur.wait_event(done)
+    for t in out.values():
+        t.record_stream(cur)
     return out
 
 

@@ -144,3 +144,22 @@ def test_heatmap_path_replays_as_a_cuda_graph(cuda_dev):
         for k in ("pose7", "rt6", "xy", "maxval"):
             a, b = out[k], eager[k]
             assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), k
+
+
+def test_heatmap_path_in_pieces_equals_one_piece(cuda_dev):
+    """A long set is decoded piece by piece on the caller's stream while a second stream solves the poses of the
+    previous piece: same bits as the one-piece call."""
+    from esa_pose_estimation_b200 import pipeline
+    B, kp, S = 23, 11, 48
+    hm, _ = make_heatmaps(15, B, kp, S, S, "gauss")
+    hm_t = torch.from_numpy(hm).to(cuda_dev)
+    model = torch.from_numpy(tango_model(kp, seed=9)).to(cuda_dev)
+    K = torch.from_numpy(np.array([[120.0, 0, 24], [0, 120.0, 24], [0, 0, 1]])).to(cuda_dev)
+    bbox = torch.rand((B, 2), dtype=torch.float64, device=cuda_dev) * 10
+    rate = torch.rand((B,), dtype=torch.float64, device=cuda_dev) + 0.5
+    one = pipeline.poses_from_heatmaps(hm_t, bbox, rate, model, K, min_k=8, chunk_frames=1000)
+    for cf in (5, 8, 22):
+        many = pipeline.poses_from_heatmaps(hm_t, bbox, rate, model, K, min_k=8, chunk_frames=cf)
+        torch.cuda.synchronize()
+        for k in one:
+            assert torch.equal(many[k].view(torch.uint8), one[k].view(torch.uint8)), (cf, k)

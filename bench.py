@@ -447,6 +447,9 @@ def run_ours(a):
         "value_batches_in_flight": {"caller_streams": n_streams, "value": poses_per_step * a.steps / (ms_streams * 1e-3),
                                     "ms_per_step": ms_streams / a.steps, "unit": UNIT},
     }
+    if a.no_e2e:                              # profiling runs: keep the line valid JSON (no NaN)
+        line["e2e"].update(value=None, ms_per_step=None)
+        line["value_batches_in_flight"].update(value=None, ms_per_step=None)
     # --- CPU baseline (oracle port) on a bounded sample, rank 0, N=1 only
     if world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1

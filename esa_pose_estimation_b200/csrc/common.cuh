@@ -56,9 +56,48 @@ struct ProfScope {
 // carve-out (60 % measured best end to end: 2.36 ms per batch vs 2.44 at 72 %, 2.57 at 100 %, 2.69 without);
 // none of them depends on L1 capacity (streaming loads, shared-memory tiles) except the compaction
 // scatter, which is handled at its launch site.
+// Tuning hooks.  The shipped library reads NO environment variables: overrides exist only in builds with
+// -DEPB_TUNING (EPB_EXTRA_NVCC_FLAGS=-DEPB_TUNING python -m esa_pose_estimation_b200.build --force), which the
+// profiling scripts under tools/ use.  Knobs: EPB_CARVEOUT, EPB_VOTE_IMPL, EPB_VOTE_ITEM, EPB_VOTE_R,
+// EPB_GATHER_SPLIT, EPB_GATHER_CTAS[_PER_SM], EPB_GATHER_LIGHT, EPB_GATHER_VSPLIT.
+inline int tuning_int(const char* name, int dflt) {
+#ifdef EPB_TUNING
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
 inline int carveout_percent() {
-  static const int pct = [] { const char* e = getenv("EPB_CARVEOUT"); return e ? atoi(e) : 60; }();
+  static const int pct = tuning_int("EPB_CARVEOUT", 60);
   return pct;
+}
+// SM count of the current device, queried once per device
+inline int device_sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    __atomic_store_n(&cached[dev], n, __ATOMIC_RELAXED);
+  }
+  return n;
+}
+// Is `ptr` page-locked host memory?  (cudaPointerGetAttributes costs ~1 us; the answer only steers which of two
+// equivalent gather kernels runs, so a one-entry per-thread cache keyed by the pointer is safe.)
+inline bool is_host_pointer(const void* ptr) {
+  static thread_local const void* last_ptr = nullptr;
+  static thread_local bool last_host = false;
+  if (ptr != last_ptr || ptr == nullptr) {
+    cudaPointerAttributes attr;
+    last_host = ptr && cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    last_ptr = ptr;
+  }
+  return last_host;
 }
 template <typename K>
 inline void prefer_max_shared(K kernel) {

@@ -136,8 +136,10 @@ struct Workspace {
   float* ratio;           // [B] max_num / fg (float32 like the reference)
   unsigned long long* off_u;  // [B] generator offset of the uniform_ draw
   unsigned long long* off_r;  // [B] generator offset of the first random_ draw
-  uint32_t* fgpix;        // [B][H*W] packed (y << 16 | x), row-major stable order
-  float2* direct;         // [B][vn][H*W] field vectors of the foreground pixels, in fgpix order
+  int32_t* ovf;           // [B] 1 if the subsample kept more pixels than the workspace holds (image dropped)
+  uint32_t* fgpix;        // [B][cap] packed (y << 16 | x), row-major stable order
+  float2* direct;         // [B][vn][cap] field vectors of the foreground pixels, in fgpix order
+  int cap;                // voting pixels per image the workspace holds (multiple of the vote tile, see voting_cap)
   float* hyp;             // [B][vn][2][HNs] x plane then y plane, HNs = HN rounded up to 4 (hyp_stride)
   int32_t* counts;        // [B][vn][HN]
   int32_t* item_off;      // [B+1] exclusive scan of ceil(tn / item_px): work list of vote_count
@@ -148,6 +150,21 @@ __device__ __forceinline__ float* hyp_plane(const Workspace& ws, int b, int vn, 
   return ws.hyp + (((size_t)b * vn + v) * 2 + c) * hyp_stride(HN);
 }
 __host__ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+// Voting pixels per image the workspace is sized for.  Without the subsample an image votes with all its
+// foreground (<= H*W).  With it (torch-compatible Philox draws; ransac_voting_gpu.py:536-540) every
+// foreground pixel is kept with probability max_num / fg, so tn ~ Binomial(fg, max_num / fg): mean max_num,
+// variance < max_num.  max_num + 8 sigma + 1024 is exceeded with probability < 1e-15 per image; an image
+// that does exceed it is dropped with status 3 (mask_scan_kernel), never written out of bounds.
+// Caller-supplied draws (`selection`, parity tests) can select anything: full size there.
+__host__ inline int voting_cap(const epb_voting_params& p) {
+  const long long HW = (long long)p.H * p.W;
+  long long cap = HW;
+  if (p.rng_mode == EPB_RNG_PHILOX && p.max_num > 0 && (long long)p.max_num < HW) {
+    const long long bound = (long long)p.max_num + (long long)(8.0 * sqrt((double)p.max_num)) + 1024;
+    if (bound < cap) cap = bound;
+  }
+  return (int)((cap + 127) / 128 * 128);
+}
 __host__ inline Workspace carve(const epb_voting_params& p, void* base) {
   Workspace w;
   const size_t B = p.B, T = ((size_t)p.H * p.W + TILE_PX - 1) / TILE_PX;
@@ -164,8 +181,10 @@ __host__ inline Workspace carve(const epb_voting_params& p, void* base) {
   w.ratio = (float*)take(B * 4);
   w.off_u = (unsigned long long*)take(B * 8);
   w.off_r = (unsigned long long*)take(B * 8);
-  w.fgpix = (uint32_t*)take(B * (size_t)p.H * p.W * 4);
-  w.direct = (float2*)take(B * p.vn * (size_t)p.H * p.W * 8);
+  w.ovf = (int32_t*)take(B * 4);
+  w.cap = voting_cap(p);
+  w.fgpix = (uint32_t*)take(B * (size_t)w.cap * 4);
+  w.direct = (float2*)take(B * p.vn * (size_t)w.cap * 8);
   w.hyp = (float*)take(B * p.vn * 2 * (size_t)hyp_stride((int)HN) * 4);
   w.counts = (int32_t*)take(B * p.vn * HN * 4);
   w.item_off = (int32_t*)take((B + 1) * 4);
@@ -282,6 +301,11 @@ mask_scan_kernel(int T, int phase, int min_num, int max_num, int allow_sub, Work
       ws.sub[b] = sub;
       ws.ratio[b] = sub ? __fdiv_rn((float)max_num, (float)total) : 2.0f;
       ws.tn[b] = live ? total : 0;
+      ws.ovf[b] = 0;
+    } else if (total > ws.cap) {
+      // the subsample kept more than the workspace holds (see voting_cap): drop the image, flagged.  The
+      // generator offsets were assigned from `live` before this pass, so the other images are unaffected.
+      ws.tn[b] = 0; ws.live[b] = 0; ws.ovf[b] = 1;
     } else {
       ws.tn[b] = total;
     }
@@ -376,7 +400,7 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
   const int v_per = (p.vn + gridDim.y - 1) / gridDim.y;
   const int v_lo = blockIdx.y * v_per, v_hi = min(p.vn, v_lo + v_per);
   if (blockIdx.y == 0) {
-    uint32_t* out = ws.fgpix + (size_t)b * HW;
+    uint32_t* out = ws.fgpix + (size_t)b * ws.cap;
 #pragma unroll
     for (int g = 0; g < 16; ++g)
       if ((mine >> g) & 1u) {
@@ -389,12 +413,12 @@ mask_scatter_kernel(const uint8_t* __restrict__ mask, int H, int W, int T, int m
     // planar field: every (image, keypoint, component) plane is one contiguous H*W array (the NCHW network
     // output): pixel px is element px of the plane.  Groups without foreground are not read at all.
     const float* base = vertex + (b / p.classes) * p.sb + seg + lane;
-    float2* dst = ws.direct + (size_t)b * p.vn * HW + wbase;
+    float2* dst = ws.direct + (size_t)b * p.vn * ws.cap + wbase;
     // host-resident field (`light`): 8 loads in flight per thread instead of 32 -- plenty for PCIe
     for (int v = v_lo; v < v_hi; ++v) {
       const float* px = base + (long long)v * p.sv;
       const float* py = px + p.sc;
-      float2* d = dst + (size_t)v * HW;
+      float2* d = dst + (size_t)v * ws.cap;
       if (!light) {
         float fx[16], fy[16];
 #pragma unroll
@@ -433,7 +457,7 @@ field_gather_kernel(const float* __restrict__ vertex, epb_voting_params p, Works
   const int b = blockIdx.y;
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (!ws.live[b] || t >= ws.tn[b]) return;
-  const size_t HW = (size_t)p.H * p.W;
+  const size_t HW = (size_t)ws.cap;
   const uint32_t q = ws.fgpix[(size_t)b * HW + t];
   const float* src = vertex + (b / p.classes) * p.sb + (long long)(q >> 16) * p.sy + (long long)(q & 0xffff) * p.sx;
   float2* dst = ws.direct + (size_t)b * p.vn * HW + t;
@@ -492,10 +516,10 @@ hypothesis_kernel(epb_voting_params p, Workspace ws, HypCtx hc,
       if (hc.rng_mode == EPB_RNG_RAW32) { t0 %= (unsigned)tn; t1 %= (unsigned)tn; }
       else { t0 = min(t0, (unsigned)tn - 1); t1 = min(t1, (unsigned)tn - 1); }
     }
-    const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
+    const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
     const uint32_t q0 = fp[t0], q1 = fp[t1];
     const int x0 = q0 & 0xffff, y0 = q0 >> 16, x1 = q1 & 0xffff, y1 = q1 >> 16;
-    const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+    const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
     const float2 d0 = dir[t0], d1 = dir[t1];
     float ix, iy;
     if (intersect_rays(d0.x, d0.y, (float)x0, (float)y0, d1.x, d1.y, (float)x1, (float)y1, &ix, &iy)) {
@@ -584,6 +608,37 @@ __host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
   return c;
 }
 
+// Constants of the tensor-core form (vote_mma_kernel; error budget in DESIGN.md section 5b).
+//   direction: n^ = n / |n| carries two independent final roundings -> rotated by <= u; beta uses 12.5 u
+//   a' terms:  5 u each (k rounded, k n^ rounded, hi/lo residual of A, of h, dropped lo*lo); A3: 4 u
+//   p  terms:  3 u each (residual of B, of h, dropped lo*lo); B3: 2 u of the FMA + 1 u residual
+//   tensor core: accumulating the 8 products in FP32 with truncation: <= CM u sum|terms| (CM = 2x the worst
+//              case measured by tools/micro/mma_tf32_probe.cu, rounded up)
+//   band w:    computed from the high halves only and with gamma A truncated to TF32: relative 2^-9 of the
+//              terms of a', i.e. gamma k 2^-8 (|h|_1 + |c|_1) in absolute terms, folded into EH; EH itself is
+//              rounded up by 2^-9 because the tensor core truncates it to TF32
+constexpr double VOTE_MMA_CM = 8.0;
+__host__ inline VoteConsts vote_consts_mma(float thresh, int H, int W) {
+  VoteConsts c;
+  const double T = (double)thresh, u = 5.9604644775390625e-08;  // 2^-24
+  c.fast_ok = 0; c.kf = 0.f; c.gamma = 0.f; c.eh_scale = 0.f; c.eh_abs = 0.f;
+  if (!(T >= 0.5 && T < 1.0)) return c;
+  const double k = sqrt((1.0 - T) * (1.0 + T)) / T;
+  const double theta = acos(T);
+  if (!(2.0 * sin(0.5 * theta) * sin(0.25 * theta) >= 12.5 * u)) return c;
+  const double beta = 12.5 * u / (T * sin(0.75 * theta));
+  const double gamma = beta * (1.0 / k + 1.0) * 1.0001 * (1.0 + 1.0 / 256.0);
+  if (!(gamma <= 0.25)) return c;
+  const double es = (1.5 * ((5.0 + VOTE_MMA_CM) * k + (3.0 + VOTE_MMA_CM)) * u + gamma * k / 256.0) * (1.0 + 1.0 / 256.0);
+  const double ea = es * (double)(H + W) + 3.5e-6 * (1.0 + k) * (1.0 + 1.0 / 256.0);
+  c.fast_ok = 1;
+  c.kf = (float)k;
+  c.gamma = nextafterf((float)gamma, INFINITY);
+  c.eh_scale = nextafterf((float)es, INFINITY);
+  c.eh_abs = nextafterf((float)ea, INFINITY);
+  return c;
+}
+
 constexpr int VOTE_QCAP = 1024;  // deferred undecided pairs per work unit (overflow is resolved in line)
 struct VoteSmem {
   float4 f[2][VOTE_TILE];  // A1 A2 B1 B2
@@ -650,8 +705,8 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
       neg[2 * q] = neg[2 * q + 1] = 0u;
     }
 
-    const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
-    const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+    const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
+    const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
     uint32_t pq[PER_THREAD];
     float pnx[PER_THREAD], pny[PER_THREAD];
 
@@ -809,6 +864,358 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 6b. vote_mma: the same exact counts with the two affine forms on the tensor cores.
+//
+// a' and p are rank-3 bilinear forms of (record, hypothesis).  Each is evaluated as ONE K = 8 TF32 MMA with
+// both operands split in a high and a low half (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is < 2^-24 of
+// the product), accumulated in FP32:
+//   record side   (A1h, A2h, A3h, A1h | A1l, A2l, A3l, A2h)         A = k n^, A3 = -k n^.c   (n^ = n / |n|)
+//   hypothesis    (hxh, hyh,  1 , hxl | hxh, hyh,  1 , hyl)         same vector for the p form (B = (-n^y, n^x), B3)
+// and the band w = gamma a' + EH[h] -- itself affine in the hypothesis -- as a K = 4 MMA of the high halves
+// (gamma A1h, gamma A2h, gamma A3h, 1) x (hxh, hyh, 1, EH[h]).  One m16n8k8 tile = 8 records x {a', p} rows x 8
+// hypotheses, so a lane finds a'(t,h) and p(t,h) of the same pair in its own accumulator registers; what is
+// left for the FP32 pipe per pair is  m = a' - |p|,  |m| > w,  and the sign-bit count: 3 instructions instead
+// of 7.  Pairs inside the band take the reference expression, exactly as in vote_count (queue + dense
+// resolution), so the counts remain the reference's integers; DESIGN.md section 5b has the error budget of
+// the split (5 u per A term, 3 u per B term) and of the tensor core's accumulation (measured,
+// tools/micro/mma_tf32_probe.cu) that EH covers.
+//
+// CTA = 8 consumer warps (64 hypotheses each: 8 n-blocks whose B fragments, bands and counters stay in
+// registers for the whole unit) + 1 producer warp.  Work unit = (item of pixels, keypoint, chunk of 512
+// hypotheses).  The producer's lane 0 streams the raw tiles (128 x float2 direction + 128 x packed pixel)
+// global -> shared with cp.async.bulk on mbarriers (TMA, no register staging); the producer warp turns a raw
+// tile into 128 48-byte records (normalisation, k-scaling, hi/lo split: ~70 instructions per record, once per
+// record and chunk) in a 3-deep ring that the consumers read as MMA A fragments.
+// ------------------------------------------------------------------------------------------
+constexpr int VM_WARPS = 8;                      // consumer warps
+constexpr int VM_NB = 8;                         // n-blocks of 8 hypotheses per consumer warp
+constexpr int VM_CHUNK = VM_WARPS * VM_NB * 8;   // 512 hypotheses per work unit
+constexpr int VM_TILE = 128;                     // records per stage
+constexpr int VM_REC_STAGES = 3;
+constexpr int VM_RAW_STAGES = 4;
+constexpr int VM_THREADS = (VM_WARPS + 1) * 32;
+constexpr int VM_QCAP = 2048;                    // deferred undecided pairs per work unit
+constexpr int VM_REC_FLOATS = 12;                // (A1h,B1h)(A2h,B2h)(A3h,B3h)(A1l,B1l)(A2l,B2l)(A3l,B3l)
+
+struct VmSmem {
+  alignas(128) float rec[VM_REC_STAGES][VM_TILE * VM_REC_FLOATS];
+  alignas(128) float2 raw_dir[VM_RAW_STAGES][VM_TILE];
+  alignas(128) uint32_t raw_pix[VM_RAW_STAGES][VM_TILE];
+  unsigned long long raw_full[VM_RAW_STAGES], rec_full[VM_REC_STAGES], rec_empty[VM_REC_STAGES];
+  unsigned q[VM_QCAP];
+  unsigned qn;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = tf32_rna(x);
+  lo = (fabsf(hi) <= FLT_MAX) ? tf32_rna(__fsub_rn(x, hi)) : 0.f;   // x - hi is exact; -inf markers keep lo = 0
+}
+__device__ __forceinline__ void mma_tf32_k8(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.f));
+}
+__device__ __forceinline__ void mma_tf32_k4(float (&d)[4], float a0, float a1, float b0) {
+  asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(b0)), "f"(0.f));
+}
+
+// one raw pixel -> the 12 floats of its record (three float4 stores)
+__device__ __forceinline__ void make_record(uint32_t q, float nx, float ny, bool in_range, float kf,
+                                            float4& o0, float4& o1, float4& o2) {
+  const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
+  const float s1 = __fmaf_rn(nx, nx, __fmul_rn(ny, ny));
+  const float n1 = __fsqrt_rn(s1);
+  // reference guard :121 (zero direction), NaN / overflowed |n|^2 (c = NaN or 0): never an inlier
+  const bool valid = in_range && !((double)n1 < 1e-6) && (s1 <= FLT_MAX);
+  float A1 = 0.f, A2 = 0.f, A3 = -INFINITY, B1 = 0.f, B2 = 0.f, B3 = 0.f;
+  if (valid) {
+    // exact power-of-two scaling first (no over/underflow in the squares), then one common factor 1/|n|: the
+    // direction of (ux, uy) differs from n's by the two final roundings only (<= u)
+    const float nm = fmaxf(fabsf(nx), fabsf(ny));
+    const float sc = __uint_as_float((254u - ((__float_as_uint(nm) >> 23) & 0xffu)) << 23);
+    const float nxs = __fmul_rn(nx, sc), nys = __fmul_rn(ny, sc);
+    const float r = __frsqrt_rn(__fmaf_rn(nxs, nxs, __fmul_rn(nys, nys)));
+    const float ux = __fmul_rn(nxs, r), uy = __fmul_rn(nys, r);
+    A1 = __fmul_rn(kf, ux);
+    A2 = __fmul_rn(kf, uy);
+    A3 = -__fmul_rn(kf, __fmaf_rn(ux, cx, __fmul_rn(uy, cy)));
+    B1 = -uy;
+    B2 = ux;
+    B3 = __fmaf_rn(uy, cx, -__fmul_rn(ux, cy));
+  }
+  float h[6], l[6];
+  tf32_split(A1, h[0], l[0]); tf32_split(B1, h[1], l[1]); tf32_split(A2, h[2], l[2]);
+  tf32_split(B2, h[3], l[3]); tf32_split(A3, h[4], l[4]); tf32_split(B3, h[5], l[5]);
+  o0 = make_float4(h[0], h[1], h[2], h[3]);
+  o1 = make_float4(h[4], h[5], l[0], l[1]);
+  o2 = make_float4(l[2], l[3], l[4], l[5]);
+}
+
+__global__ void __launch_bounds__(VM_THREADS, 2)
+vote_mma_kernel(epb_voting_params p, Workspace ws, VoteConsts vc, int item_px, int chunks) {
+  __shared__ VmSmem sm;
+  const int HN = p.hn * p.rounds;
+  const int B = p.B;
+  const int* __restrict__ item_off = ws.item_off;
+  const long long total = (long long)item_off[B] * p.vn * chunks;
+  const long long unit = blockIdx.x;
+  if (unit >= total) return;
+  const int per_item = p.vn * chunks;
+  const int item = (int)(unit / per_item);
+  const int rem = (int)(unit - (long long)item * per_item);
+  const int v = rem / chunks, chunk = rem - v * chunks;
+  int lo = 0, hi = B;  // largest b with item_off[b] <= item
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (item_off[mid] <= item) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int tn = ws.tn[b];
+  const int t_begin = (item - item_off[b]) * item_px, t_end = min(tn, t_begin + item_px);
+  const int ntiles = (t_end - t_begin + VM_TILE - 1) / VM_TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
+  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
+  const float* hypx = hyp_plane(ws, b, p.vn, v, HN, 0);
+  const float* hypy = hyp_plane(ws, b, p.vn, v, HN, 1);
+  const float T = p.inlier_thresh;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < VM_RAW_STAGES; ++i) mbar_init(&sm.raw_full[i], 1);
+#pragma unroll
+    for (int i = 0; i < VM_REC_STAGES; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], VM_WARPS); }
+    sm.qn = 0u;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // the reference expression (IEEE sqrt / div) for pixel t of this image against hypothesis (hx, hy)
+  auto exact_vote = [&](int t, float hx, float hy) -> bool {
+    if (t >= t_end) return false;                         // padding record
+    const uint32_t q = __ldg(fp + t);
+    const float2 d = __ldg(dir + t);
+    return vote_exact((float)(q & 0xffff), (float)(q >> 16), d.x, d.y, dir_norm(d.x, d.y), hx, hy, T);
+  };
+
+  if (warp == VM_WARPS) {
+    // ---------------- producer: TMA raw tiles in, records out
+    auto issue = [&](int i) {   // lane 0 only.  Whole tiles: the workspace rows are padded to VM_TILE pixels
+      const int rs = i % VM_RAW_STAGES;
+      mbar_expect_tx(&sm.raw_full[rs], VM_TILE * 12);
+      bulk_g2s(sm.raw_dir[rs], dir + t_begin + (size_t)i * VM_TILE, VM_TILE * 8, &sm.raw_full[rs]);
+      bulk_g2s(sm.raw_pix[rs], fp + t_begin + (size_t)i * VM_TILE, VM_TILE * 4, &sm.raw_full[rs]);
+    };
+    if (lane == 0)
+      for (int i = 0; i < min(VM_RAW_STAGES, ntiles); ++i) issue(i);
+    for (int i = 0; i < ntiles; ++i) {
+      const int rs = i % VM_RAW_STAGES, s = i % VM_REC_STAGES;
+      mbar_wait(&sm.raw_full[rs], (unsigned)(i / VM_RAW_STAGES) & 1u);
+      if (i >= VM_REC_STAGES) mbar_wait(&sm.rec_empty[s], (unsigned)(i / VM_REC_STAGES - 1) & 1u);
+      float4* out = reinterpret_cast<float4*>(sm.rec[s]);
+#pragma unroll
+      for (int k = 0; k < VM_TILE / 32; ++k) {
+        const int r = k * 32 + lane;
+        const float2 d = sm.raw_dir[rs][r];
+        float4 o0, o1, o2;
+        make_record(sm.raw_pix[rs][r], d.x, d.y, t_begin + i * VM_TILE + r < t_end, vc.kf, o0, o1, o2);
+        out[r * 3 + 0] = o0; out[r * 3 + 1] = o1; out[r * 3 + 2] = o2;
+      }
+      __syncwarp();   // every lane has consumed raw stage rs and written its records
+      if (lane == 0) {
+        mbar_arrive(&sm.rec_full[s]);
+        if (i + VM_RAW_STAGES < ntiles) issue(i + VM_RAW_STAGES);
+      }
+    }
+  } else {
+    // ---------------- consumers
+    const int g = lane >> 2, j = lane & 3;
+    const int hbase = chunk * VM_CHUNK + warp * (VM_NB * 8);
+    const bool active = hbase < HN;    // warp-uniform
+    float fb0[VM_NB], fb1[VM_NB], fbw[VM_NB];
+    unsigned neg[VM_NB][2];
+#pragma unroll
+    for (int nb = 0; nb < VM_NB; ++nb) {
+      const int h = hbase + 8 * nb + g;            // the hypothesis this lane feeds into the B fragments (n = g)
+      float hx = 0.f, hy = 0.f;
+      if (h < HN) { hx = hypx[h]; hy = hypy[h]; }
+      float hxh, hxl, hyh, hyl;
+      tf32_split(hx, hxh, hxl); tf32_split(hy, hyh, hyl);
+      // non-finite or huge hypotheses: undecided against every pixel -> reference expression
+      const float habs = __fadd_ru(fabsf(hx), fabsf(hy));
+      const float eh = (habs <= 1e15f) ? __fmaf_ru(vc.eh_scale, habs, vc.eh_abs) : INFINITY;
+      fb0[nb] = j == 0 ? hxh : j == 1 ? hyh : j == 2 ? 1.f : hxl;
+      fb1[nb] = j == 0 ? hxh : j == 1 ? hyh : j == 2 ? 1.f : hyl;
+      fbw[nb] = j == 3 ? eh : fb0[nb];
+      neg[nb][0] = neg[nb][1] = 0u;
+    }
+    const int q0 = j < 3 ? j : 0, q1 = j < 3 ? j + 3 : 1;   // record pairs of this lane's k and k + 4
+    const float gam = vc.gamma;
+    unsigned* const qn_ptr = &sm.qn;
+    unsigned* const q_ptr = sm.q;
+    // undecided pair -> queue (with the sign the fast loop is about to count); a full queue resolves in line
+    auto defer = [&](int t_rel, int h_rel, float& m) {
+      const unsigned pos = atomicAdd(qn_ptr, 1u);
+      if (pos < (unsigned)VM_QCAP) {
+        q_ptr[pos] = ((unsigned)t_rel << 10) | ((unsigned)h_rel << 1) | (__float_as_uint(m) >> 31);
+      } else {
+        const int h = chunk * VM_CHUNK + h_rel;
+        const bool in = h < HN && exact_vote(t_begin + t_rel, __ldg(hypx + h), __ldg(hypy + h));
+        m = in ? 1.0f : -1.0f;
+      }
+    };
+    for (int i = 0; i < ntiles; ++i) {
+      const int s = i % VM_REC_STAGES;
+      mbar_wait(&sm.rec_full[s], (unsigned)(i / VM_REC_STAGES) & 1u);
+      if (active) {
+        const float2* rec2 = reinterpret_cast<const float2*>(sm.rec[s]);
+#pragma unroll 1
+        for (int st = 0; st < VM_TILE / 16; ++st) {
+          // A fragments: records st*16 + g (rows g: a', g + 8: p) and st*16 + 8 + g
+          const float2* ra = rec2 + (st * 16 + g) * 6;
+          const float2* rb = ra + 8 * 6;
+          const float2 x0 = ra[q0], x1 = ra[q1], y0 = rb[q0], y1 = rb[q1];
+          const float A0[4] = {x0.x, x0.y, x1.x, x1.y};
+          const float A1[4] = {y0.x, y0.y, y1.x, y1.y};
+          // band rows (16 records): k = j -> gamma * (A1h, A2h, A3h), k = 3 -> 1
+          const float w_a0 = j < 3 ? __fmul_rn(gam, x0.x) : 1.f;
+          const float w_a1 = j < 3 ? __fmul_rn(gam, y0.x) : 1.f;
+          const int t_rel0 = i * VM_TILE + st * 16 + g;
+#pragma unroll
+          for (int nb = 0; nb < VM_NB; nb += 2) {
+            float d00[4], d10[4], d01[4], d11[4], w0[4], w1[4];
+            mma_tf32_k8(d00, A0, fb0[nb], fb1[nb]);
+            mma_tf32_k8(d10, A1, fb0[nb], fb1[nb]);
+            mma_tf32_k4(w0, w_a0, w_a1, fbw[nb]);
+            mma_tf32_k8(d01, A0, fb0[nb + 1], fb1[nb + 1]);
+            mma_tf32_k8(d11, A1, fb0[nb + 1], fb1[nb + 1]);
+            mma_tf32_k4(w1, w_a0, w_a1, fbw[nb + 1]);
+            // m[e]: e bit 0 = column (hypothesis 2j / 2j + 1), bit 1 = record (g / g + 8), bit 2 = n-block
+            float m[8];
+            m[0] = __fsub_rn(d00[0], fabsf(d00[2])); m[1] = __fsub_rn(d00[1], fabsf(d00[3]));
+            m[2] = __fsub_rn(d10[0], fabsf(d10[2])); m[3] = __fsub_rn(d10[1], fabsf(d10[3]));
+            m[4] = __fsub_rn(d01[0], fabsf(d01[2])); m[5] = __fsub_rn(d01[1], fabsf(d01[3]));
+            m[6] = __fsub_rn(d11[0], fabsf(d11[2])); m[7] = __fsub_rn(d11[1], fabsf(d11[3]));
+            const float w[8] = {w0[0], w0[1], w0[2], w0[3], w1[0], w1[1], w1[2], w1[3]};
+            bool amb = false;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) amb |= !(fabsf(m[e]) > w[e]);
+            if (amb) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (!(fabsf(m[e]) > w[e]))
+                  defer(t_rel0 + ((e & 2) ? 8 : 0), warp * (VM_NB * 8) + 8 * (nb + (e >> 2)) + 2 * j + (e & 1), m[e]);
+            }
+            neg[nb][0] += (__float_as_uint(m[0]) >> 31) + (__float_as_uint(m[2]) >> 31);
+            neg[nb][1] += (__float_as_uint(m[1]) >> 31) + (__float_as_uint(m[3]) >> 31);
+            neg[nb + 1][0] += (__float_as_uint(m[4]) >> 31) + (__float_as_uint(m[6]) >> 31);
+            neg[nb + 1][1] += (__float_as_uint(m[5]) >> 31) + (__float_as_uint(m[7]) >> 31);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.rec_empty[s]);
+    }
+    if (active) {
+      // every record visited beyond t_end is a padding record (m = -inf, or queued and corrected), so the
+      // difference below is the number of voting pixels
+      int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
+      const int visited = ntiles * VM_TILE;
+#pragma unroll
+      for (int nb = 0; nb < VM_NB; ++nb)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          unsigned n = neg[nb][c];
+          n += __shfl_xor_sync(FULL, n, 4);
+          n += __shfl_xor_sync(FULL, n, 8);
+          n += __shfl_xor_sync(FULL, n, 16);
+          const int h = hbase + 8 * nb + 2 * j + c;
+          const int cnt = visited - (int)n;
+          if (g == 0 && h < HN && cnt != 0) atomicAdd(out + h, cnt);
+        }
+    }
+  }
+  __syncthreads();   // every enqueue precedes this barrier
+  {
+    // deferred pairs: one per thread, reference expression, correction of the count the fast loop produced
+    int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
+    const unsigned nq = min(sm.qn, (unsigned)VM_QCAP);
+    for (unsigned e = threadIdx.x; e < nq; e += VM_THREADS) {
+      const unsigned ent = sm.q[e];
+      const int t = t_begin + (int)(ent >> 10);
+      const int h = chunk * VM_CHUNK + (int)((ent >> 1) & 511u);
+      if (h >= HN) continue;
+      const bool fast_inlier = (ent & 1u) == 0u;
+      const bool exact = exact_vote(t, __ldg(hypx + h), __ldg(hypy + h));
+      if (exact != fast_inlier) atomicAdd(out + h, exact ? 1 : -1);
+    }
+  }
+}
+
+// Thresholds the band test cannot serve (outside [0.5, 1), or so close to 1 that the band is wider than a
+// quarter of a'): the reference expression for every pair, one thread per hypothesis, pixels staged through
+// shared memory.  ~35 issue slots per pair; never on the default thresholds.
+__global__ void __launch_bounds__(256)
+vote_exact_kernel(epb_voting_params p, Workspace ws) {
+  const int HN = p.hn * p.rounds;
+  const int b = blockIdx.z, v = blockIdx.y, h = blockIdx.x * 256 + threadIdx.x;
+  if (!ws.live[b]) return;
+  const int tn = ws.tn[b];
+  __shared__ float4 s_px[256];   // cx, cy, nx, ny
+  __shared__ float s_n1[256];
+  const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
+  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
+  float hx = 0.f, hy = 0.f;
+  if (h < HN) { hx = hyp_plane(ws, b, p.vn, v, HN, 0)[h]; hy = hyp_plane(ws, b, p.vn, v, HN, 1)[h]; }
+  int cnt = 0;
+  for (int t0 = 0; t0 < tn; t0 += 256) {
+    const int t = t0 + threadIdx.x;
+    if (t < tn) {
+      const uint32_t q = __ldg(fp + t);
+      const float2 d = __ldg(dir + t);
+      s_px[threadIdx.x] = make_float4((float)(q & 0xffff), (float)(q >> 16), d.x, d.y);
+      s_n1[threadIdx.x] = dir_norm(d.x, d.y);
+    }
+    __syncthreads();
+    const int n = min(256, tn - t0);
+    for (int r = 0; r < n; ++r) {
+      const float4 px = s_px[r];
+      cnt += vote_exact(px.x, px.y, px.z, px.w, s_n1[r], hx, hy, p.inlier_thresh);
+    }
+    __syncthreads();
+  }
+  if (h < HN) ws.counts[((size_t)b * p.vn + v) * HN + h] = cnt;
+}
+
 // work list of vote_count: item_off[b] = number of pixel items of the images before b.
 __global__ void __launch_bounds__(256)
 vote_items_kernel(int B, int item_px, Workspace ws) {
@@ -890,9 +1297,10 @@ winner_refine_kernel(epb_voting_params p, Workspace ws,
   int32_t* st = status ? status + (size_t)b * p.vn + v : nullptr;
   if (!ws.live[b]) {
     if (threadIdx.x == 0) {
-      *out = make_float2(0.f, 0.f);
-      if (aux) *aux = p.mode == EPB_VOTE_V4 ? 1.0f : 0.0f;
-      if (st) *st = 1;
+      const bool ovf = ws.ovf[b] != 0;   // dropped by the workspace bound (voting_cap): NaN, status 3
+      *out = ovf ? make_float2(NAN, NAN) : make_float2(0.f, 0.f);
+      if (aux) *aux = ovf ? NAN : (p.mode == EPB_VOTE_V4 ? 1.0f : 0.0f);
+      if (st) *st = ovf ? 3 : 1;
     }
     return;
   }
@@ -924,8 +1332,8 @@ winner_refine_kernel(epb_voting_params p, Workspace ws,
   }
   __syncthreads();
   float2 win = s_pt;
-  const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
-  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+  const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
+  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
   if (p.mode == EPB_VOTE_V1) {   // ransac_voting_layer (:10-97): the winning hypothesis itself
     if (threadIdx.x == 0) { *out = win; if (st) *st = 0; }
     return;
@@ -1031,7 +1439,9 @@ distribution_kernel(epb_voting_params p, Workspace ws, const float* __restrict__
   const bool with_mean = p.mode == EPB_VOTE_DISTRIBUTION_WITH_MEAN;
   if (!ws.live[b]) {
     // hypotheses 0, ratios 1 (:273-278): mean 0 (or the given mean), cov = mean mean^T * sum/(sum[+1e-3])
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && ws.ovf[b]) {
+      mo[0] = mo[1] = NAN; co[0] = co[1] = co[2] = co[3] = NAN;
+    } else if (threadIdx.x == 0) {
       if (with_mean) {
         const double mx = mean_in[((size_t)b * p.vn + v) * 2], my = mean_in[((size_t)b * p.vn + v) * 2 + 1];
         const double s = (double)HN, den = s + 1e-3;
@@ -1168,8 +1578,8 @@ motion_mean_kernel(epb_voting_params p, Workspace ws, float* __restrict__ pts) {
   const int v = blockIdx.x, b = blockIdx.y;
   __shared__ double s_red[2 * 8];
   const int tn = ws.live[b] ? ws.tn[b] : 0;
-  const uint32_t* fp = ws.fgpix + (size_t)b * p.H * p.W;
-  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * p.H * p.W;
+  const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
+  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
   double acc[2] = {0, 0};
   for (int t = threadIdx.x; t < tn; t += 256) {
     const uint32_t q = __ldg(fp + t);
@@ -1281,6 +1691,7 @@ static void voting_kernel_attributes() {
   prefer_max_shared(mask_scatter_kernel<true>); prefer_max_shared(mask_scatter_kernel<false>);
   prefer_max_shared(field_gather_kernel); prefer_max_shared(hypothesis_kernel); prefer_max_shared(vote_items_kernel);
   prefer_max_shared(vote_count_kernel<2>); prefer_max_shared(vote_count_kernel<4>); prefer_max_shared(vote_count_kernel<8>);
+  prefer_max_shared(vote_mma_kernel); prefer_max_shared(vote_exact_kernel);
   prefer_max_shared(counts_export_kernel); prefer_max_shared(winner_refine_kernel); prefer_max_shared(distribution_kernel);
   prefer_max_shared(motion_mean_kernel);
   prefer_max_shared(generate_hypothesis_kernel); prefer_max_shared(voting_for_hypothesis_kernel);
@@ -1288,7 +1699,51 @@ static void voting_kernel_attributes() {
   cudaGetLastError();
 }
 
-static int g_vote_r_large = 4;  // hypotheses per thread when HN > 512 (measured at HN = 2048: 1.48 ms with 4, 1.66 ms with 8)
+static int g_vote_r_large = 4;
+
+// Work units of the vote kernels: (item of <= item_px voting pixels, keypoint, hypothesis chunk), listed on the
+// device (vote_items_kernel) so that ragged batches balance without a host sync; CTAs beyond the list exit at once.
+static int launch_vote_mma(const epb_voting_params& p, const Workspace& ws, const VoteConsts& vc, cudaStream_t s) {
+  const int HN = p.hn * p.rounds;
+  const int chunks = (HN + VM_CHUNK - 1) / VM_CHUNK;
+  const long long slots = 2LL * device_sm_count();          // two 9-warp CTAs per SM
+  // items small enough that the work list is several waves long, large enough to amortise a unit's prologue
+  // (64 B-fragment registers per lane, barrier set-up) and its tail (queue resolution, 16 count atomics per lane)
+  const int tn_max = ws.cap;
+  int item_px = 16 * VM_TILE;
+  while (item_px > VM_TILE && (long long)p.B * p.vn * chunks * ((tn_max + item_px - 1) / item_px) < 4 * slots) item_px >>= 1;
+  { const int forced = tuning_int("EPB_VOTE_ITEM", 0); if (forced >= VM_TILE && forced % VM_TILE == 0) item_px = forced; }
+  const long long max_units = (long long)p.B * p.vn * chunks * ((tn_max + item_px - 1) / item_px);
+  if (max_units > 0x7fffffffLL) return EPB_ERR_INVALID;
+  vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
+  EPB_RETURN_IF(check_launch());
+  EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
+  vote_mma_kernel<<<(unsigned)max_units, VM_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+  return check_launch();
+}
+
+static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, cudaStream_t s) {
+  const int HN = p.hn * p.rounds;
+  int R = HN <= 256 ? 2 : (HN <= 512 ? 4 : g_vote_r_large);
+  { const int forced = tuning_int("EPB_VOTE_R", 0); if (forced == 2 || forced == 4 || forced == 8) R = forced; }
+  const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
+  const long long slots = (long long)device_sm_count() * (R <= 4 ? 8 : 4);
+  int item_px = 4 * VOTE_TILE;
+  while (item_px > VOTE_TILE &&
+         (long long)p.B * p.vn * chunks * ((ws.cap + item_px - 1) / item_px) < 4 * slots) item_px >>= 1;
+  const long long max_units = (long long)p.B * p.vn * chunks * ((ws.cap + item_px - 1) / item_px);
+  if (max_units > 0x7fffffffLL) return EPB_ERR_INVALID;
+  const unsigned grid = (unsigned)max_units;
+  const VoteConsts vc = vote_consts(p.inlier_thresh, p.H, p.W);
+  vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
+  EPB_RETURN_IF(check_launch());
+  EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
+  if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+  else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+  else vote_count_kernel<8><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+  return check_launch();
+}
+  // hypotheses per thread when HN > 512 (measured at HN = 2048: 1.48 ms with 4, 1.66 ms with 8)
 
 static bool params_ok(const epb_voting_params* p) {
   if (!p) return false;
@@ -1370,43 +1825,41 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
   }
   // planar field (NCHW network output seen through vertex_layer_reshape): gather fused into the scatter
   const bool planar = p.sx == 1 && p.sy == p.W;   // pixel px of a plane is element px: scalar, line-coalesced reads
-  cudaPointerAttributes attr;
-  const bool host_field = cudaPointerGetAttributes(&attr, io->vertex) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
+  const bool host_field = is_host_pointer(io->vertex);
   // The fused form exists for host-resident fields (whole 128-byte lines over PCIe).  In HBM the plain pair --
   // compaction of the coordinates, then one thread per compacted pixel gathering its keypoints -- is faster
   // (compaction class 0.113 -> 0.082 ms on config[1]): the fused kernel spends its instructions on the 3/4 of the
-  // 32-pixel groups that hold no foreground.  EPB_GATHER_SPLIT=0 forces the fused kernel (profiling).
-  static const int split_knob = [] { const char* e = getenv("EPB_GATHER_SPLIT"); return e ? atoi(e) : 1; }();
-  if (planar && !(split_knob && !host_field)) {
-    int dev_id = 0, sm_n = 148;
-    cudaGetDevice(&dev_id);
-    cudaDeviceGetAttribute(&sm_n, cudaDevAttrMultiProcessorCount, dev_id);
+  // 32-pixel groups that hold no foreground.
+  if (planar && !(tuning_int("EPB_GATHER_SPLIT", 1) && !host_field)) {
+    const int sm_n = device_sm_count();
     const long long work = (long long)T * p.B;
-    static const int per_sm = [] { const char* e = getenv("EPB_GATHER_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
-    static const int total_cap = [] { const char* e = getenv("EPB_GATHER_CTAS"); return e ? atoi(e) : 0; }();
+    const int per_sm = tuning_int("EPB_GATHER_CTAS_PER_SM", 1), total_cap = tuning_int("EPB_GATHER_CTAS", 0);
     const long long cap = total_cap > 0 ? total_cap : (long long)sm_n * (per_sm > 0 ? per_sm : 1);
     const unsigned g = (unsigned)(host_field && work > cap ? cap : work);
-    static const int light_knob = [] { const char* e = getenv("EPB_GATHER_LIGHT"); return e ? atoi(e) : 1; }();
+    const int light_knob = tuning_int("EPB_GATHER_LIGHT", 1);
     // device-resident field: split the keypoints over gridDim.y so that the grid is several waves deep
     // (the gather is HBM-bound and each CTA is register-heavy); host field: one slim persistent wave
-    static const int vsplit_knob = [] { const char* e = getenv("EPB_GATHER_VSPLIT"); return e ? atoi(e) : 0; }();
+    const int vsplit_knob = tuning_int("EPB_GATHER_VSPLIT", 0);
     int vsplit = 1;
     if (!host_field) {
       vsplit = vsplit_knob > 0 ? vsplit_knob : (work < 16LL * sm_n ? 2 : 1);
       if (vsplit > p.vn) vsplit = p.vn;
     }
-    // The scatter is the kernel that shares SMs with vote_count in the host pipeline, where it must ask for a
+    // The scatter is the kernel that shares SMs with the vote kernel in the host pipeline, where it must ask for a
     // large shared-memory carve-out (common.cuh); alone on the device it is 20 % faster with the default
     // split (88 vs 111 us), so the preference follows the kind of field (attribute read at launch).
     {
       static int current[64];   // per device: 0 unknown, 1 default split, 2 large carve-out (the call is not free)
       const int want = host_field ? 2 : 1;
-      if (dev_id >= 0 && dev_id < 64 && current[dev_id] != want) {
+      int dev_id = 0;
+      cudaGetDevice(&dev_id);
+      if (dev_id >= 0 && dev_id < 64 && __atomic_load_n(&current[dev_id], __ATOMIC_ACQUIRE) != want) {
+        // (two threads racing here both set the same attribute value for their `want`; the last one wins and the
+        // cache then says so -- the attribute is a preference, never a correctness matter)
         cudaFuncSetAttribute(reinterpret_cast<const void*>(mask_scatter_kernel<true>),
                              cudaFuncAttributePreferredSharedMemoryCarveout,
                              host_field ? carveout_percent() : (int)cudaSharedmemCarveoutDefault);
-        current[dev_id] = want;
+        __atomic_store_n(&current[dev_id], want, __ATOMIC_RELEASE);
       }
     }
     mask_scatter_kernel<true><<<dim3(g, vsplit), 256, 0, s>>>(io->mask, p.H, p.W, T, p.mask_mode, ws, sc, io->vertex, p,
@@ -1442,59 +1895,16 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     EPB_RETURN_IF(check_launch());
   }
   {
-    // equal-sized work units (pixel item x keypoint x hypothesis chunk), listed on the device
-    int R = HN <= 256 ? 2 : (HN <= 512 ? 4 : g_vote_r_large);
-    {  // tuning hook (profiling only): EPB_VOTE_R=2|4|8 overrides the hypotheses per thread
-      static const int forced = [] { const char* e = getenv("EPB_VOTE_R"); return e ? atoi(e) : 0; }();
-      if (forced == 2 || forced == 4 || forced == 8) R = forced;
-    }
-    const int chunks = (HN + VOTE_THREADS * R - 1) / (VOTE_THREADS * R);
-    int dev = 0, sms = 148, occ = 0;
-    EPB_RETURN_IF(check_api(cudaGetDevice(&dev)));
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (R == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_count_kernel<2>, VOTE_THREADS, 0);
-    else if (R == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_count_kernel<4>, VOTE_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, vote_count_kernel<8>, VOTE_THREADS, 0);
-    if (occ < 1) occ = 1;
-    const long long slots = (long long)sms * occ;
-    // items small enough that the work list is several waves long, large enough to amortise a unit
-    int item_px = 4 * VOTE_TILE;
-    while (item_px > VOTE_TILE &&
-           (long long)p.B * p.vn * chunks * ((HW + item_px - 1) / item_px) < 4 * slots) item_px >>= 1;
-    {  // tuning hook (profiling only)
-      static const int forced = [] { const char* e = getenv("EPB_VOTE_ITEM"); return e ? atoi(e) : 0; }();
-      if (forced >= VOTE_TILE) item_px = forced;
-    }
-    const long long max_units = (long long)p.B * p.vn * chunks * ((HW + item_px - 1) / item_px);
-    if (max_units > 0x7fffffffLL) return EPB_ERR_INVALID;
-    const unsigned grid = (unsigned)max_units;   // units beyond the device-side total exit at once
-    const VoteConsts vc = vote_consts(p.inlier_thresh, p.H, p.W);
-    vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
-    EPB_RETURN_IF(check_launch());
-    EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
-    // Split runs overlap this kernel with the gather stage of the next batch chunk on a high-priority
-    // stream.  Its small kernels can only start when an SM has registers to spare, so the vote CTAs are
-    // held two below full occupancy there (unused dynamic shared memory is the occupancy knob; measured:
-    // gather 0.75 -> 0.58 ms per chunk under a concurrent vote, vote 0.68 -> 0.61 ms).
-    size_t pad = 0;
-    static const int pad_always = [] { const char* e = getenv("EPB_VOTE_HEADROOM_ALWAYS"); return e ? atoi(e) : 0; }();
-    // (only a host-resident field keeps the gather stage busy long enough to matter: it reads over PCIe)
-    cudaPointerAttributes vattr;
-    const bool host_field = io->vertex && cudaPointerGetAttributes(&vattr, io->vertex) == cudaSuccess &&
-                            vattr.type == cudaMemoryTypeHost;
-    if (((p.stage == EPB_STAGE_VOTE && host_field) || pad_always) && occ >= 6) {   // (kernels at <= 5 CTAs/SM leave that room anyway)
-      static const int knob = [] { const char* e = getenv("EPB_VOTE_HEADROOM"); return e ? atoi(e) : 2; }();
-      const int want = occ - knob;
-      const size_t per_sm = 227 * 1024, used = sizeof(VoteSmem) + 1024;
-      if (knob > 0 && want >= 1 && per_sm / (size_t)want > used) pad = per_sm / (size_t)(want + 1) + 1024 > used
-                                                                          ? per_sm / (size_t)(want + 1) + 1024 - used : 0;
-      if (pad + used > 48 * 1024) pad = 0;       // stay within the default dynamic shared memory limit
-    }
+    const VoteConsts vc = vote_consts_mma(p.inlier_thresh, p.H, p.W);
+    int impl = vc.fast_ok ? 1 : 0;   // 1: tensor-core form; 0: reference expression per pair (odd thresholds)
+    if (tuning_int("EPB_VOTE_IMPL", 1) == 2) impl = 2;   // the round-1 FP32 kernel (A/B measurements)
     ProfScope ps(PROF_VOTE_COUNT, s);
-    if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
-    else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
-    else vote_count_kernel<8><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
-    EPB_RETURN_IF(check_launch());
+    if (impl == 1) EPB_RETURN_IF(launch_vote_mma(p, ws, vc, s));
+    else if (impl == 2) EPB_RETURN_IF(launch_vote_ffma(p, ws, s));
+    else {
+      vote_exact_kernel<<<dim3((HN + 255) / 256, p.vn, p.B), 256, 0, s>>>(p, ws);
+      EPB_RETURN_IF(check_launch());
+    }
   }
   if (io->counts) {
     const long long n = (long long)p.B * HN * p.vn;

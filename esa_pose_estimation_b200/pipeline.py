@@ -125,7 +125,9 @@ def poses_from_vertex(mask, vertex, p3d_model, K, round_hyp_num=512, inlier_thre
     the foreground and reads the field of piece i+1 in place over PCIe while a second stream votes
     piece i; a third (high-priority) stream solves the poses once the keypoints are there, so the
     latency-bound pose solve of one call runs under the voting of the next.  The caller's stream waits
-    for the poses: results are valid on the caller's stream, as usual.
+    for the poses: results are valid on the caller's stream, as usual.  Pinned host inputs are READ BY THE
+    GPU after this call returns: leave them untouched until the caller's stream has passed the returned
+    tensors (e.g. `torch.cuda.current_stream().synchronize()` or an event recorded after the call).
 
     `pipelined=True` sends DEVICE-resident inputs down the same route (one piece).  Within one caller
     stream that changes nothing (the inputs of call n+1 are ordered after the results of call n), but
@@ -226,11 +228,15 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
             d[k] = t[s:e]
         return d
 
-    # device-resident arguments were produced on the current stream; host buffers need no ordering
+    # Everything the side streams touch is ordered after the caller's stream: device-resident arguments were
+    # produced there, pinned HOST buffers may still be the target of a non_blocking copy_ queued there, and the
+    # workspaces come from the caching allocator's pool of that stream (a block it just freed may have work
+    # pending on `cur`).  One event wait per call; the overlap with the PREVIOUS call's voting is unaffected
+    # (that call is already queued on the side streams).
     ready = torch.cuda.Event()
     ready.record(cur)
-    if mask.is_cuda or vertex.is_cuda or per_image:
-        gs.wait_event(ready)
+    gs.wait_event(ready)
+    vs.wait_event(ready)
     events, masks_d = [], []
     with torch.cuda.stream(gs):
         for i, (s, e) in enumerate(bounds):
@@ -245,8 +251,6 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
             events.append(ev)
             masks_d.append(m_d)
     kps = []
-    if per_image:                             # explicit index tensors were produced on the caller's stream
-        vs.wait_event(ready)
     with torch.cuda.stream(vs):
         for i, (s, e) in enumerate(bounds):
             vs.wait_event(events[i])

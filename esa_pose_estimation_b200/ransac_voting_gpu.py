@@ -40,7 +40,10 @@ def vertex_layer_reshape(vertex_pred):
 
 
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
+    # one scratch buffer per (device, caller stream): calls issued on different streams (or from threads that
+    # use different streams) never share fgpix / records / counts, and a buffer is only ever freed into the pool
+    # of the stream that used it
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty((int(nbytes * 1.25) + 4096,), dtype=torch.uint8, device=device)

@@ -30,15 +30,16 @@ class SubmissionWriter:
             self._append(name, p[:4], p[4:7], real)
 
     def export(self, out_dir='', suffix=None):
-        """Rows sorted by filename, test rows before real-test rows (submission.py:36-52)."""
-        sorted_test = sorted(self.test_results, key=lambda k: k['filename'])
-        sorted_real_test = sorted(self.real_test_results, key=lambda k: k['filename'])
-        if suffix is None:
-            suffix = datetime.now().strftime("%Y%m%d-%H%M")
-        submission_path = os.path.join(out_dir, 'submission_{}.csv'.format(suffix))
-        with open(submission_path, 'w') as f:
-            csv_writer = csv.writer(f, lineterminator='\n')
-            for result in (sorted_test + sorted_real_test):
-                csv_writer.writerow([result['filename'], *(result['q'] + result['r'])])
-        print('Submission saved to {}.'.format(submission_path))
-        return submission_path
+        """Writes `submission_<suffix>.csv` into out_dir: one `filename, q0..q3, r0..r2` row per estimate,
+        synthetic-test rows first and real-test rows after them, each group ordered by file name
+        (the file the ESA server expects; interface of submission.py:36-52).  Returns the path."""
+        from itertools import chain
+        tag = suffix if suffix is not None else datetime.now().strftime("%Y%m%d-%H%M")
+        path = os.path.join(out_dir, 'submission_%s.csv' % tag)
+        by_name = lambda rec: rec['filename']
+        rows = ([rec['filename'], *rec['q'], *rec['r']]
+                for rec in chain(sorted(self.test_results, key=by_name), sorted(self.real_test_results, key=by_name)))
+        with open(path, 'w', newline='') as fh:
+            csv.writer(fh, lineterminator='\n').writerows(rows)
+        print('Submission saved to {}.'.format(path))
+        return path

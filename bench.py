@@ -55,31 +55,10 @@ def workload_name(a):
 
 # ----------------------------------------------------------------------------- synthetic data
 def make_batch_numpy(a, seed, n_images):
-    """Structured SPEED-like crops: the 11 keypoints are the projections of the Tango model under a
-    random pose, scaled into the crop; field = unit vectors towards them + 2 deg noise."""
-    from tests.synth import ellipse_mask, make_pose_case, tango_model
-    rng = np.random.default_rng(seed)
-    s, vn = a.size, a.vn
-    model = tango_model(vn, seed=9)
-    ys, xs = np.mgrid[0:s, 0:s].astype(np.float32)
-    mask = np.zeros((n_images, s, s), np.uint8)
-    vertex = np.zeros((n_images, 2 * vn, s, s), np.float32)
-    kcrop = np.zeros((n_images, vn, 2))
-    geom = np.zeros((n_images, 3))      # bbox x, bbox y, rate  (val.py:180 un-crop: ori = pred/rate + (x, y))
-    for i in range(n_images):
-        c = make_pose_case(seed * 100003 + i, vn, 0.0, 0, model=model)
-        lo, hi = c["p2d"].min(0), c["p2d"].max(0)
-        size = (hi - lo).max() * 1.6 + 8
-        org = (lo + hi) / 2 - size / 2
-        rate = s / size
-        kc = (c["p2d"] - org) * rate
-        kcrop[i] = kc
-        geom[i] = (org[0], org[1], rate)
-        mask[i] = ellipse_mask(s, s, a.fg, rng, jitter=0.03)
-        for v in range(vn):
-            ang = np.arctan2(kc[v, 1] - ys, kc[v, 0] - xs) + np.float32(np.deg2rad(2.0)) * rng.standard_normal((s, s), dtype=np.float32)
-            vertex[i, 2 * v] = np.cos(ang)
-            vertex[i, 2 * v + 1] = np.sin(ang)
+    """Structured SPEED-like crops (tests/synth.py: make_pose_field): the keypoints are the projections of the
+    Tango model under a random pose, scaled into the crop; field = unit vectors towards them + 2 deg noise."""
+    from tests.synth import make_pose_field
+    mask, vertex, model, geom, kcrop, _, _ = make_pose_field(seed, n_images, a.size, a.vn, a.fg, noise_deg=2.0)
     return mask, vertex, model, geom, kcrop
 
 

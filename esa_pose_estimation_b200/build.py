@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libesa_pose_b200.so")
-SOURCES = ["api.cu", "decode.cu", "voting.cu", "pose.cu"]
+SOURCES = ["api.cu", "decode.cu", "voting.cu", "pose.cu", "metrics.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "esa_pose_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -33,15 +33,15 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, lib=LIB, extra_flags=(), objdir="build"):
+    if not force and lib == LIB and not needs_build():
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, objdir), exist_ok=True)
     for s in SOURCES:
-        obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", obj]
+        obj = os.path.join(HERE, objdir, s.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -52,12 +52,27 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s:\n%s" % (s, out))
         if verbose and out.strip():
             print(out)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("link failed:\n" + out.stdout + out.stderr)
-    return LIB
+    return lib
+
+
+TUNING_LIB = os.path.join(HERE, "libesa_pose_b200_tuning.so")
+
+
+def build_tuning(force=False, verbose=False):
+    """The same library with -DEPB_TUNING: the only build in which the EPB_* environment knobs of
+    csrc/common.cuh exist.  Used by the measurement scripts under tools/, never by the package."""
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    if not force and os.path.exists(TUNING_LIB) and all(
+            os.path.getmtime(d) <= os.path.getmtime(TUNING_LIB) for d in deps if os.path.exists(d)):
+        return TUNING_LIB
+    return build(force=True, verbose=verbose, lib=TUNING_LIB, extra_flags=["-DEPB_TUNING"], objdir="build/tuning")
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--tuning" in sys.argv:
+        print(build_tuning(force="--force" in sys.argv, verbose=True))

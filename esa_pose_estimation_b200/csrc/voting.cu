@@ -24,6 +24,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -163,7 +164,7 @@ __host__ inline int voting_cap(const epb_voting_params& p) {
     const long long bound = (long long)p.max_num + (long long)(8.0 * sqrt((double)p.max_num)) + 1024;
     if (bound < cap) cap = bound;
   }
-  return (int)((cap + 127) / 128 * 128);
+  return (int)((cap + 255) / 256 * 256);   // whole vote tiles (TMA copies never leave a row)
 }
 __host__ inline Workspace carve(const epb_voting_params& p, void* base) {
   Workspace w;
@@ -583,6 +584,7 @@ struct VoteConsts {
   float gamma;      // relative half-width of the undecided band, in units of a'
   float eh_scale;   // EH[h] = eh_scale * (|hx| + |hy|) + eh_abs
   float eh_abs;
+  float s1_min;     // (vote_mma.cuh) smallest |n|^2 whose IEEE root passes the reference's guard (double)norm1 >= 1e-6
 };
 __host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
   VoteConsts c;
@@ -608,41 +610,15 @@ __host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
   return c;
 }
 
-// Constants of the tensor-core form (vote_mma_kernel; error budget in DESIGN.md section 5b).
-//   direction: n^ = n / |n| carries two independent final roundings -> rotated by <= u; beta uses 12.5 u
-//   a' terms:  5 u each (k rounded, k n^ rounded, hi/lo residual of A, of h, dropped lo*lo); A3: 4 u
-//   p  terms:  3 u each (residual of B, of h, dropped lo*lo); B3: 2 u of the FMA + 1 u residual
-//   tensor core: accumulating the 8 products in FP32 with truncation: <= CM u sum|terms| (CM = 2x the worst
-//              case measured by tools/micro/mma_tf32_probe.cu, rounded up)
-//   band w:    computed from the high halves only and with gamma A truncated to TF32: relative 2^-9 of the
-//              terms of a', i.e. gamma k 2^-8 (|h|_1 + |c|_1) in absolute terms, folded into EH; EH itself is
-//              rounded up by 2^-9 because the tensor core truncates it to TF32
-constexpr double VOTE_MMA_CM = 8.0;
-__host__ inline VoteConsts vote_consts_mma(float thresh, int H, int W) {
-  VoteConsts c;
-  const double T = (double)thresh, u = 5.9604644775390625e-08;  // 2^-24
-  c.fast_ok = 0; c.kf = 0.f; c.gamma = 0.f; c.eh_scale = 0.f; c.eh_abs = 0.f;
-  if (!(T >= 0.5 && T < 1.0)) return c;
-  const double k = sqrt((1.0 - T) * (1.0 + T)) / T;
-  const double theta = acos(T);
-  if (!(2.0 * sin(0.5 * theta) * sin(0.25 * theta) >= 12.5 * u)) return c;
-  const double beta = 12.5 * u / (T * sin(0.75 * theta));
-  const double gamma = beta * (1.0 / k + 1.0) * 1.0001 * (1.0 + 1.0 / 256.0);
-  if (!(gamma <= 0.25)) return c;
-  const double es = (1.5 * ((5.0 + VOTE_MMA_CM) * k + (3.0 + VOTE_MMA_CM)) * u + gamma * k / 256.0) * (1.0 + 1.0 / 256.0);
-  const double ea = es * (double)(H + W) + 3.5e-6 * (1.0 + k) * (1.0 + 1.0 / 256.0);
-  c.fast_ok = 1;
-  c.kf = (float)k;
-  c.gamma = nextafterf((float)gamma, INFINITY);
-  c.eh_scale = nextafterf((float)es, INFINITY);
-  c.eh_abs = nextafterf((float)ea, INFINITY);
-  return c;
-}
-
 constexpr int VOTE_QCAP = 1024;  // deferred undecided pairs per work unit (overflow is resolved in line)
+constexpr int VOTE_RAW_STAGES = 2;
 struct VoteSmem {
   float4 f[2][VOTE_TILE];  // A1 A2 B1 B2
   float2 g[2][VOTE_TILE];  // A3 B3
+  // raw tiles (field vector + packed pixel of VOTE_TILE voting pixels) as the TMA delivers them
+  alignas(128) float2 raw_dir[VOTE_RAW_STAGES][VOTE_TILE];
+  alignas(128) uint32_t raw_pix[VOTE_RAW_STAGES][VOTE_TILE];
+  unsigned long long raw_full[VOTE_RAW_STAGES];
   unsigned q[VOTE_QCAP];   // undecided (pixel, hypothesis) pairs: t_rel << 11 | thread << 4 | r << 1 | sign(m)
   unsigned qn;
 };
@@ -707,25 +683,29 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
 
     const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
     const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
-    uint32_t pq[PER_THREAD];
-    float pnx[PER_THREAD], pny[PER_THREAD];
-
-    auto prefetch = [&](int t0) {
-#pragma unroll
-      for (int k = 0; k < PER_THREAD; ++k) {
-        const int t = t0 + k * VOTE_THREADS + threadIdx.x;
-        if (t < t_end) {
-          const float2 d = __ldg(dir + t);
-          pq[k] = __ldg(fp + t); pnx[k] = d.x; pny[k] = d.y;
-        } else { pq[k] = 0xffffffffu; pnx[k] = 0.f; pny[k] = 0.f; }
-      }
+    // Tiles arrive by TMA: thread 0 issues two bulk copies per tile (cp.async.bulk global -> shared, completion
+    // counted in bytes on an mbarrier), always whole tiles -- the workspace rows are padded to VOTE_TILE pixels, the
+    // records beyond t_end are marked as padding by index.  No register staging: a tile is in flight for a whole
+    // tile of compute (~11 k cycles) before anybody looks at it.
+    const int ntiles = (t_end - t_begin + VOTE_TILE - 1) / VOTE_TILE;
+    auto tma_issue = [&](int i) {   // thread 0
+      const int rs = i % VOTE_RAW_STAGES;
+      mbar_expect_tx(&sm.raw_full[rs], VOTE_TILE * 12);
+      bulk_g2s(sm.raw_dir[rs], dir + t_begin + (size_t)i * VOTE_TILE, VOTE_TILE * 8, &sm.raw_full[rs]);
+      bulk_g2s(sm.raw_pix[rs], fp + t_begin + (size_t)i * VOTE_TILE, VOTE_TILE * 4, &sm.raw_full[rs]);
     };
-    auto stage = [&](int buf) {
+
+    // records of tile i (raw stage i % VOTE_RAW_STAGES) -> record buffer `buf`
+    auto stage = [&](int i, int buf) {
+      const int rs = i % VOTE_RAW_STAGES;
+      mbar_wait(&sm.raw_full[rs], (unsigned)(i / VOTE_RAW_STAGES) & 1u);
 #pragma unroll
       for (int k = 0; k < PER_THREAD; ++k) {
-        const uint32_t q = pq[k];
+        const int slot_in = k * VOTE_THREADS + threadIdx.x;
+        const uint32_t q = (t_begin + i * VOTE_TILE + slot_in < t_end) ? sm.raw_pix[rs][slot_in] : 0xffffffffu;
+        const float2 dn = sm.raw_dir[rs][slot_in];
         const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
-        const float nx = pnx[k], ny = pny[k];
+        const float nx = dn.x, ny = dn.y;
         const float s1 = __fmaf_rn(nx, nx, __fmul_rn(ny, ny));
         const float n1 = __fsqrt_rn(s1);
         // reference guard :121 (zero direction), NaN / overflowed |n|^2 (c = NaN or 0): never an inlier
@@ -793,13 +773,20 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
     };
 
     int buf = 0;
-    prefetch(t_begin);
-    if (threadIdx.x == 0) sm.qn = 0u;
-    stage(0);
+    if (threadIdx.x == 0) {
+      sm.qn = 0u;
+#pragma unroll
+      for (int i = 0; i < VOTE_RAW_STAGES; ++i) mbar_init(&sm.raw_full[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (int i = 0; i < min(VOTE_RAW_STAGES, ntiles); ++i) tma_issue(i);
+    }
     __syncthreads();
-    for (int t0 = t_begin; t0 < t_end; t0 += VOTE_TILE) {
+    stage(0, 0);
+    __syncthreads();
+    // raw stage 0 is free again (everybody has staged tile 0)
+    if (threadIdx.x == 0 && VOTE_RAW_STAGES < ntiles) tma_issue(VOTE_RAW_STAGES);
+    for (int t0 = t_begin, ti = 0; t0 < t_end; t0 += VOTE_TILE, ++ti) {
       const bool more = t0 + VOTE_TILE < t_end;
-      if (more) prefetch(t0 + VOTE_TILE);
       const int nrec = min(VOTE_TILE, t_end - t0);
       const float4* fr = sm.f[buf];
       const float2* gr = sm.g[buf];
@@ -830,8 +817,10 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
 #pragma unroll
           for (int r = 0; r < R; ++r) neg[r] += __float_as_uint(m[j][r]) >> 31;
       }
-      if (more) stage(buf ^ 1);
+      if (more) stage(ti + 1, buf ^ 1);
       __syncthreads();
+      // everybody has staged tile ti + 1: its raw stage takes the tile VOTE_RAW_STAGES further on
+      if (threadIdx.x == 0 && ti + 1 + VOTE_RAW_STAGES < ntiles) tma_issue(ti + 1 + VOTE_RAW_STAGES);
       buf ^= 1;
     }
 
@@ -860,323 +849,6 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
       // the padding and the difference below is the number of voting pixels
       const int c = visited - (int)neg[r];
       if (h < HN && c != 0) atomicAdd(out + h, c);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// 6b. vote_mma: the same exact counts with the two affine forms on the tensor cores.
-//
-// a' and p are rank-3 bilinear forms of (record, hypothesis).  Each is evaluated as ONE K = 8 TF32 MMA with
-// both operands split in a high and a low half (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is < 2^-24 of
-// the product), accumulated in FP32:
-//   record side   (A1h, A2h, A3h, A1h | A1l, A2l, A3l, A2h)         A = k n^, A3 = -k n^.c   (n^ = n / |n|)
-//   hypothesis    (hxh, hyh,  1 , hxl | hxh, hyh,  1 , hyl)         same vector for the p form (B = (-n^y, n^x), B3)
-// and the band w = gamma a' + EH[h] -- itself affine in the hypothesis -- as a K = 4 MMA of the high halves
-// (gamma A1h, gamma A2h, gamma A3h, 1) x (hxh, hyh, 1, EH[h]).  One m16n8k8 tile = 8 records x {a', p} rows x 8
-// hypotheses, so a lane finds a'(t,h) and p(t,h) of the same pair in its own accumulator registers; what is
-// left for the FP32 pipe per pair is  m = a' - |p|,  |m| > w,  and the sign-bit count: 3 instructions instead
-// of 7.  Pairs inside the band take the reference expression, exactly as in vote_count (queue + dense
-// resolution), so the counts remain the reference's integers; DESIGN.md section 5b has the error budget of
-// the split (5 u per A term, 3 u per B term) and of the tensor core's accumulation (measured,
-// tools/micro/mma_tf32_probe.cu) that EH covers.
-//
-// CTA = 8 consumer warps (64 hypotheses each: 8 n-blocks whose B fragments, bands and counters stay in
-// registers for the whole unit) + 1 producer warp.  Work unit = (item of pixels, keypoint, chunk of 512
-// hypotheses).  The producer's lane 0 streams the raw tiles (128 x float2 direction + 128 x packed pixel)
-// global -> shared with cp.async.bulk on mbarriers (TMA, no register staging); the producer warp turns a raw
-// tile into 128 48-byte records (normalisation, k-scaling, hi/lo split: ~70 instructions per record, once per
-// record and chunk) in a 3-deep ring that the consumers read as MMA A fragments.
-// ------------------------------------------------------------------------------------------
-constexpr int VM_WARPS = 8;                      // consumer warps
-constexpr int VM_NB = 8;                         // n-blocks of 8 hypotheses per consumer warp
-constexpr int VM_CHUNK = VM_WARPS * VM_NB * 8;   // 512 hypotheses per work unit
-constexpr int VM_TILE = 128;                     // records per stage
-constexpr int VM_REC_STAGES = 3;
-constexpr int VM_RAW_STAGES = 4;
-constexpr int VM_THREADS = (VM_WARPS + 1) * 32;
-constexpr int VM_QCAP = 2048;                    // deferred undecided pairs per work unit
-constexpr int VM_REC_FLOATS = 12;                // (A1h,B1h)(A2h,B2h)(A3h,B3h)(A1l,B1l)(A2l,B2l)(A3l,B3l)
-
-struct VmSmem {
-  alignas(128) float rec[VM_REC_STAGES][VM_TILE * VM_REC_FLOATS];
-  alignas(128) float2 raw_dir[VM_RAW_STAGES][VM_TILE];
-  alignas(128) uint32_t raw_pix[VM_RAW_STAGES][VM_TILE];
-  unsigned long long raw_full[VM_RAW_STAGES], rec_full[VM_REC_STAGES], rec_empty[VM_REC_STAGES];
-  unsigned q[VM_QCAP];
-  unsigned qn;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP + SYNCS)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float tf32_rna(float x) {
-  unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
-}
-__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
-  hi = tf32_rna(x);
-  lo = (fabsf(hi) <= FLT_MAX) ? tf32_rna(__fsub_rn(x, hi)) : 0.f;   // x - hi is exact; -inf markers keep lo = 0
-}
-__device__ __forceinline__ void mma_tf32_k8(float (&d)[4], const float (&a)[4], float b0, float b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
-                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.f));
-}
-__device__ __forceinline__ void mma_tf32_k4(float (&d)[4], float a0, float a1, float b0) {
-  asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
-               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(__float_as_uint(a0)), "r"(__float_as_uint(a1)), "r"(__float_as_uint(b0)), "f"(0.f));
-}
-
-// one raw pixel -> the 12 floats of its record (three float4 stores)
-__device__ __forceinline__ void make_record(uint32_t q, float nx, float ny, bool in_range, float kf,
-                                            float4& o0, float4& o1, float4& o2) {
-  const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
-  const float s1 = __fmaf_rn(nx, nx, __fmul_rn(ny, ny));
-  const float n1 = __fsqrt_rn(s1);
-  // reference guard :121 (zero direction), NaN / overflowed |n|^2 (c = NaN or 0): never an inlier
-  const bool valid = in_range && !((double)n1 < 1e-6) && (s1 <= FLT_MAX);
-  float A1 = 0.f, A2 = 0.f, A3 = -INFINITY, B1 = 0.f, B2 = 0.f, B3 = 0.f;
-  if (valid) {
-    // exact power-of-two scaling first (no over/underflow in the squares), then one common factor 1/|n|: the
-    // direction of (ux, uy) differs from n's by the two final roundings only (<= u)
-    const float nm = fmaxf(fabsf(nx), fabsf(ny));
-    const float sc = __uint_as_float((254u - ((__float_as_uint(nm) >> 23) & 0xffu)) << 23);
-    const float nxs = __fmul_rn(nx, sc), nys = __fmul_rn(ny, sc);
-    const float r = __frsqrt_rn(__fmaf_rn(nxs, nxs, __fmul_rn(nys, nys)));
-    const float ux = __fmul_rn(nxs, r), uy = __fmul_rn(nys, r);
-    A1 = __fmul_rn(kf, ux);
-    A2 = __fmul_rn(kf, uy);
-    A3 = -__fmul_rn(kf, __fmaf_rn(ux, cx, __fmul_rn(uy, cy)));
-    B1 = -uy;
-    B2 = ux;
-    B3 = __fmaf_rn(uy, cx, -__fmul_rn(ux, cy));
-  }
-  float h[6], l[6];
-  tf32_split(A1, h[0], l[0]); tf32_split(B1, h[1], l[1]); tf32_split(A2, h[2], l[2]);
-  tf32_split(B2, h[3], l[3]); tf32_split(A3, h[4], l[4]); tf32_split(B3, h[5], l[5]);
-  o0 = make_float4(h[0], h[1], h[2], h[3]);
-  o1 = make_float4(h[4], h[5], l[0], l[1]);
-  o2 = make_float4(l[2], l[3], l[4], l[5]);
-}
-
-__global__ void __launch_bounds__(VM_THREADS, 2)
-vote_mma_kernel(epb_voting_params p, Workspace ws, VoteConsts vc, int item_px, int chunks) {
-  __shared__ VmSmem sm;
-  const int HN = p.hn * p.rounds;
-  const int B = p.B;
-  const int* __restrict__ item_off = ws.item_off;
-  const long long total = (long long)item_off[B] * p.vn * chunks;
-  const long long unit = blockIdx.x;
-  if (unit >= total) return;
-  const int per_item = p.vn * chunks;
-  const int item = (int)(unit / per_item);
-  const int rem = (int)(unit - (long long)item * per_item);
-  const int v = rem / chunks, chunk = rem - v * chunks;
-  int lo = 0, hi = B;  // largest b with item_off[b] <= item
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (item_off[mid] <= item) lo = mid; else hi = mid;
-  }
-  const int b = lo;
-  const int tn = ws.tn[b];
-  const int t_begin = (item - item_off[b]) * item_px, t_end = min(tn, t_begin + item_px);
-  const int ntiles = (t_end - t_begin + VM_TILE - 1) / VM_TILE;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
-  const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
-  const float* hypx = hyp_plane(ws, b, p.vn, v, HN, 0);
-  const float* hypy = hyp_plane(ws, b, p.vn, v, HN, 1);
-  const float T = p.inlier_thresh;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < VM_RAW_STAGES; ++i) mbar_init(&sm.raw_full[i], 1);
-#pragma unroll
-    for (int i = 0; i < VM_REC_STAGES; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], VM_WARPS); }
-    sm.qn = 0u;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // the reference expression (IEEE sqrt / div) for pixel t of this image against hypothesis (hx, hy)
-  auto exact_vote = [&](int t, float hx, float hy) -> bool {
-    if (t >= t_end) return false;                         // padding record
-    const uint32_t q = __ldg(fp + t);
-    const float2 d = __ldg(dir + t);
-    return vote_exact((float)(q & 0xffff), (float)(q >> 16), d.x, d.y, dir_norm(d.x, d.y), hx, hy, T);
-  };
-
-  if (warp == VM_WARPS) {
-    // ---------------- producer: TMA raw tiles in, records out
-    auto issue = [&](int i) {   // lane 0 only.  Whole tiles: the workspace rows are padded to VM_TILE pixels
-      const int rs = i % VM_RAW_STAGES;
-      mbar_expect_tx(&sm.raw_full[rs], VM_TILE * 12);
-      bulk_g2s(sm.raw_dir[rs], dir + t_begin + (size_t)i * VM_TILE, VM_TILE * 8, &sm.raw_full[rs]);
-      bulk_g2s(sm.raw_pix[rs], fp + t_begin + (size_t)i * VM_TILE, VM_TILE * 4, &sm.raw_full[rs]);
-    };
-    if (lane == 0)
-      for (int i = 0; i < min(VM_RAW_STAGES, ntiles); ++i) issue(i);
-    for (int i = 0; i < ntiles; ++i) {
-      const int rs = i % VM_RAW_STAGES, s = i % VM_REC_STAGES;
-      mbar_wait(&sm.raw_full[rs], (unsigned)(i / VM_RAW_STAGES) & 1u);
-      if (i >= VM_REC_STAGES) mbar_wait(&sm.rec_empty[s], (unsigned)(i / VM_REC_STAGES - 1) & 1u);
-      float4* out = reinterpret_cast<float4*>(sm.rec[s]);
-#pragma unroll
-      for (int k = 0; k < VM_TILE / 32; ++k) {
-        const int r = k * 32 + lane;
-        const float2 d = sm.raw_dir[rs][r];
-        float4 o0, o1, o2;
-        make_record(sm.raw_pix[rs][r], d.x, d.y, t_begin + i * VM_TILE + r < t_end, vc.kf, o0, o1, o2);
-        out[r * 3 + 0] = o0; out[r * 3 + 1] = o1; out[r * 3 + 2] = o2;
-      }
-      __syncwarp();   // every lane has consumed raw stage rs and written its records
-      if (lane == 0) {
-        mbar_arrive(&sm.rec_full[s]);
-        if (i + VM_RAW_STAGES < ntiles) issue(i + VM_RAW_STAGES);
-      }
-    }
-  } else {
-    // ---------------- consumers
-    const int g = lane >> 2, j = lane & 3;
-    const int hbase = chunk * VM_CHUNK + warp * (VM_NB * 8);
-    const bool active = hbase < HN;    // warp-uniform
-    float fb0[VM_NB], fb1[VM_NB], fbw[VM_NB];
-    unsigned neg[VM_NB][2];
-#pragma unroll
-    for (int nb = 0; nb < VM_NB; ++nb) {
-      const int h = hbase + 8 * nb + g;            // the hypothesis this lane feeds into the B fragments (n = g)
-      float hx = 0.f, hy = 0.f;
-      if (h < HN) { hx = hypx[h]; hy = hypy[h]; }
-      float hxh, hxl, hyh, hyl;
-      tf32_split(hx, hxh, hxl); tf32_split(hy, hyh, hyl);
-      // non-finite or huge hypotheses: undecided against every pixel -> reference expression
-      const float habs = __fadd_ru(fabsf(hx), fabsf(hy));
-      const float eh = (habs <= 1e15f) ? __fmaf_ru(vc.eh_scale, habs, vc.eh_abs) : INFINITY;
-      fb0[nb] = j == 0 ? hxh : j == 1 ? hyh : j == 2 ? 1.f : hxl;
-      fb1[nb] = j == 0 ? hxh : j == 1 ? hyh : j == 2 ? 1.f : hyl;
-      fbw[nb] = j == 3 ? eh : fb0[nb];
-      neg[nb][0] = neg[nb][1] = 0u;
-    }
-    const int q0 = j < 3 ? j : 0, q1 = j < 3 ? j + 3 : 1;   // record pairs of this lane's k and k + 4
-    const float gam = vc.gamma;
-    unsigned* const qn_ptr = &sm.qn;
-    unsigned* const q_ptr = sm.q;
-    // undecided pair -> queue (with the sign the fast loop is about to count); a full queue resolves in line
-    auto defer = [&](int t_rel, int h_rel, float& m) {
-      const unsigned pos = atomicAdd(qn_ptr, 1u);
-      if (pos < (unsigned)VM_QCAP) {
-        q_ptr[pos] = ((unsigned)t_rel << 10) | ((unsigned)h_rel << 1) | (__float_as_uint(m) >> 31);
-      } else {
-        const int h = chunk * VM_CHUNK + h_rel;
-        const bool in = h < HN && exact_vote(t_begin + t_rel, __ldg(hypx + h), __ldg(hypy + h));
-        m = in ? 1.0f : -1.0f;
-      }
-    };
-    for (int i = 0; i < ntiles; ++i) {
-      const int s = i % VM_REC_STAGES;
-      mbar_wait(&sm.rec_full[s], (unsigned)(i / VM_REC_STAGES) & 1u);
-      if (active) {
-        const float2* rec2 = reinterpret_cast<const float2*>(sm.rec[s]);
-#pragma unroll 1
-        for (int st = 0; st < VM_TILE / 16; ++st) {
-          // A fragments: records st*16 + g (rows g: a', g + 8: p) and st*16 + 8 + g
-          const float2* ra = rec2 + (st * 16 + g) * 6;
-          const float2* rb = ra + 8 * 6;
-          const float2 x0 = ra[q0], x1 = ra[q1], y0 = rb[q0], y1 = rb[q1];
-          const float A0[4] = {x0.x, x0.y, x1.x, x1.y};
-          const float A1[4] = {y0.x, y0.y, y1.x, y1.y};
-          // band rows (16 records): k = j -> gamma * (A1h, A2h, A3h), k = 3 -> 1
-          const float w_a0 = j < 3 ? __fmul_rn(gam, x0.x) : 1.f;
-          const float w_a1 = j < 3 ? __fmul_rn(gam, y0.x) : 1.f;
-          const int t_rel0 = i * VM_TILE + st * 16 + g;
-#pragma unroll
-          for (int nb = 0; nb < VM_NB; nb += 2) {
-            float d00[4], d10[4], d01[4], d11[4], w0[4], w1[4];
-            mma_tf32_k8(d00, A0, fb0[nb], fb1[nb]);
-            mma_tf32_k8(d10, A1, fb0[nb], fb1[nb]);
-            mma_tf32_k4(w0, w_a0, w_a1, fbw[nb]);
-            mma_tf32_k8(d01, A0, fb0[nb + 1], fb1[nb + 1]);
-            mma_tf32_k8(d11, A1, fb0[nb + 1], fb1[nb + 1]);
-            mma_tf32_k4(w1, w_a0, w_a1, fbw[nb + 1]);
-            // m[e]: e bit 0 = column (hypothesis 2j / 2j + 1), bit 1 = record (g / g + 8), bit 2 = n-block
-            float m[8];
-            m[0] = __fsub_rn(d00[0], fabsf(d00[2])); m[1] = __fsub_rn(d00[1], fabsf(d00[3]));
-            m[2] = __fsub_rn(d10[0], fabsf(d10[2])); m[3] = __fsub_rn(d10[1], fabsf(d10[3]));
-            m[4] = __fsub_rn(d01[0], fabsf(d01[2])); m[5] = __fsub_rn(d01[1], fabsf(d01[3]));
-            m[6] = __fsub_rn(d11[0], fabsf(d11[2])); m[7] = __fsub_rn(d11[1], fabsf(d11[3]));
-            const float w[8] = {w0[0], w0[1], w0[2], w0[3], w1[0], w1[1], w1[2], w1[3]};
-            bool amb = false;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) amb |= !(fabsf(m[e]) > w[e]);
-            if (amb) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (!(fabsf(m[e]) > w[e]))
-                  defer(t_rel0 + ((e & 2) ? 8 : 0), warp * (VM_NB * 8) + 8 * (nb + (e >> 2)) + 2 * j + (e & 1), m[e]);
-            }
-            neg[nb][0] += (__float_as_uint(m[0]) >> 31) + (__float_as_uint(m[2]) >> 31);
-            neg[nb][1] += (__float_as_uint(m[1]) >> 31) + (__float_as_uint(m[3]) >> 31);
-            neg[nb + 1][0] += (__float_as_uint(m[4]) >> 31) + (__float_as_uint(m[6]) >> 31);
-            neg[nb + 1][1] += (__float_as_uint(m[5]) >> 31) + (__float_as_uint(m[7]) >> 31);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.rec_empty[s]);
-    }
-    if (active) {
-      // every record visited beyond t_end is a padding record (m = -inf, or queued and corrected), so the
-      // difference below is the number of voting pixels
-      int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
-      const int visited = ntiles * VM_TILE;
-#pragma unroll
-      for (int nb = 0; nb < VM_NB; ++nb)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          unsigned n = neg[nb][c];
-          n += __shfl_xor_sync(FULL, n, 4);
-          n += __shfl_xor_sync(FULL, n, 8);
-          n += __shfl_xor_sync(FULL, n, 16);
-          const int h = hbase + 8 * nb + 2 * j + c;
-          const int cnt = visited - (int)n;
-          if (g == 0 && h < HN && cnt != 0) atomicAdd(out + h, cnt);
-        }
-    }
-  }
-  __syncthreads();   // every enqueue precedes this barrier
-  {
-    // deferred pairs: one per thread, reference expression, correction of the count the fast loop produced
-    int32_t* out = ws.counts + ((size_t)b * p.vn + v) * HN;
-    const unsigned nq = min(sm.qn, (unsigned)VM_QCAP);
-    for (unsigned e = threadIdx.x; e < nq; e += VM_THREADS) {
-      const unsigned ent = sm.q[e];
-      const int t = t_begin + (int)(ent >> 10);
-      const int h = chunk * VM_CHUNK + (int)((ent >> 1) & 511u);
-      if (h >= HN) continue;
-      const bool fast_inlier = (ent & 1u) == 0u;
-      const bool exact = exact_vote(t, __ldg(hypx + h), __ldg(hypy + h));
-      if (exact != fast_inlier) atomicAdd(out + h, exact ? 1 : -1);
     }
   }
 }
@@ -1244,6 +916,10 @@ vote_items_kernel(int B, int item_px, Workspace ws) {
   }
   if (threadIdx.x == 0) ws.item_off[B] = s_carry;
 }
+
+#ifdef EPB_TUNING
+#include "vote_mma.cuh"   // 6b. the tensor-core form of the vote test: measured, not adopted
+#endif
 
 // counts_ws [B][vn][HN] -> user layout [B][HN][vn]
 __global__ void counts_export_kernel(epb_voting_params p, Workspace ws, int32_t* __restrict__ out) {
@@ -1690,8 +1366,14 @@ static void voting_kernel_attributes() {
   prefer_max_shared(mask_count_kernel); prefer_max_shared(mask_scan_kernel); prefer_max_shared(rng_offsets_kernel);
   prefer_max_shared(mask_scatter_kernel<true>); prefer_max_shared(mask_scatter_kernel<false>);
   prefer_max_shared(field_gather_kernel); prefer_max_shared(hypothesis_kernel); prefer_max_shared(vote_items_kernel);
-  prefer_max_shared(vote_count_kernel<2>); prefer_max_shared(vote_count_kernel<4>); prefer_max_shared(vote_count_kernel<8>);
-  prefer_max_shared(vote_mma_kernel); prefer_max_shared(vote_exact_kernel);
+  // vote_count: 8 CTAs x 22.6 KB (records + TMA raw stages + queue) need 181 KB of shared memory per SM
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(vote_count_kernel<2>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(vote_count_kernel<4>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(vote_count_kernel<8>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  prefer_max_shared(vote_exact_kernel);
+#ifdef EPB_TUNING
+  prefer_max_shared(vote_mma_kernel);
+#endif
   prefer_max_shared(counts_export_kernel); prefer_max_shared(winner_refine_kernel); prefer_max_shared(distribution_kernel);
   prefer_max_shared(motion_mean_kernel);
   prefer_max_shared(generate_hypothesis_kernel); prefer_max_shared(voting_for_hypothesis_kernel);
@@ -1701,28 +1383,9 @@ static void voting_kernel_attributes() {
 
 static int g_vote_r_large = 4;
 
-// Work units of the vote kernels: (item of <= item_px voting pixels, keypoint, hypothesis chunk), listed on the
+// Work units of the vote kernel: (item of <= item_px voting pixels, keypoint, hypothesis chunk), listed on the
 // device (vote_items_kernel) so that ragged batches balance without a host sync; CTAs beyond the list exit at once.
-static int launch_vote_mma(const epb_voting_params& p, const Workspace& ws, const VoteConsts& vc, cudaStream_t s) {
-  const int HN = p.hn * p.rounds;
-  const int chunks = (HN + VM_CHUNK - 1) / VM_CHUNK;
-  const long long slots = 2LL * device_sm_count();          // two 9-warp CTAs per SM
-  // items small enough that the work list is several waves long, large enough to amortise a unit's prologue
-  // (64 B-fragment registers per lane, barrier set-up) and its tail (queue resolution, 16 count atomics per lane)
-  const int tn_max = ws.cap;
-  int item_px = 16 * VM_TILE;
-  while (item_px > VM_TILE && (long long)p.B * p.vn * chunks * ((tn_max + item_px - 1) / item_px) < 4 * slots) item_px >>= 1;
-  { const int forced = tuning_int("EPB_VOTE_ITEM", 0); if (forced >= VM_TILE && forced % VM_TILE == 0) item_px = forced; }
-  const long long max_units = (long long)p.B * p.vn * chunks * ((tn_max + item_px - 1) / item_px);
-  if (max_units > 0x7fffffffLL) return EPB_ERR_INVALID;
-  vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
-  EPB_RETURN_IF(check_launch());
-  EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
-  vote_mma_kernel<<<(unsigned)max_units, VM_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
-  return check_launch();
-}
-
-static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, cudaStream_t s) {
+static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, const VoteConsts& vc, cudaStream_t s) {
   const int HN = p.hn * p.rounds;
   int R = HN <= 256 ? 2 : (HN <= 512 ? 4 : g_vote_r_large);
   { const int forced = tuning_int("EPB_VOTE_R", 0); if (forced == 2 || forced == 4 || forced == 8) R = forced; }
@@ -1734,7 +1397,6 @@ static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, cud
   const long long max_units = (long long)p.B * p.vn * chunks * ((ws.cap + item_px - 1) / item_px);
   if (max_units > 0x7fffffffLL) return EPB_ERR_INVALID;
   const unsigned grid = (unsigned)max_units;
-  const VoteConsts vc = vote_consts(p.inlier_thresh, p.H, p.W);
   vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
   EPB_RETURN_IF(check_launch());
   EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
@@ -1895,15 +1557,25 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     EPB_RETURN_IF(check_launch());
   }
   {
-    const VoteConsts vc = vote_consts_mma(p.inlier_thresh, p.H, p.W);
-    int impl = vc.fast_ok ? 1 : 0;   // 1: tensor-core form; 0: reference expression per pair (odd thresholds)
-    if (tuning_int("EPB_VOTE_IMPL", 1) == 2) impl = 2;   // the round-1 FP32 kernel (A/B measurements)
+    const VoteConsts vc = vote_consts(p.inlier_thresh, p.H, p.W);
     ProfScope ps(PROF_VOTE_COUNT, s);
-    if (impl == 1) EPB_RETURN_IF(launch_vote_mma(p, ws, vc, s));
-    else if (impl == 2) EPB_RETURN_IF(launch_vote_ffma(p, ws, s));
-    else {
-      vote_exact_kernel<<<dim3((HN + 255) / 256, p.vn, p.B), 256, 0, s>>>(p, ws);
-      EPB_RETURN_IF(check_launch());
+    bool done = false;
+#ifdef EPB_TUNING
+    if (tuning_int("EPB_VOTE_IMPL", 0) == 1) {   // the tensor-core form (vote_mma.cuh), A/B measurements only
+      VoteConsts vm = vote_consts_mma(p.inlier_thresh, p.H, p.W);
+      if (vm.fast_ok) {
+        vm.fast_ok |= tuning_int("EPB_VM_DEBUG", 0) << 8;
+        EPB_RETURN_IF(launch_vote_mma(p, ws, vm, s));
+        done = true;
+      }
+    }
+#endif
+    if (!done) {
+      if (vc.fast_ok) EPB_RETURN_IF(launch_vote_ffma(p, ws, vc, s));
+      else {   // thresholds the band test cannot serve: the reference expression for every pair
+        vote_exact_kernel<<<dim3((HN + 255) / 256, p.vn, p.B), 256, 0, s>>>(p, ws);
+        EPB_RETURN_IF(check_launch());
+      }
     }
   }
   if (io->counts) {

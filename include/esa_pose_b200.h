@@ -27,6 +27,9 @@
  *   epb_pose_pipeline                val.py:172-228 per-frame glue, batched (select, un-crop,
  *                                    EPnP-RANSAC, LM, quaternion)
  *   epb_esa_score                    demo.py:295-310
+ *   epb_pose_metrics                 evaluation.py:340-411 projection_2d[_sym], add_metric[_sym], cm_degree_5_metric
+ *   epb_nearest_point_idx            lib/utils/extend_utils/extend_utils.py:40 find_nearest_point_idx
+ *                                    (-> src/nearest_neighborhood.cu:48-121)
  *   epb_cov_to_weights               lib/utils/evaluation_utils.py:170-181 cov -> inv(sqrtm(cov)) weights
  *   epb_p3p                          lib/utils/extend_utils/extend_utils.py:83-95 (and :147-156): cv2.solvePnP(P3P)
  *                                    on the four best-weighted correspondences
@@ -251,6 +254,23 @@ int epb_pose_pipeline(const float* preds, const float* maxvals, const double* bb
 /* demo.py:295-310: pose7 pred/gt [B,7] f32 -> score_t [B], score_r [B] f64. */
 int epb_esa_score(const float* pose7_pred, const float* pose7_gt, int B, double* score_t,
                   double* score_r, void* stream);
+
+/* ------------------------------------------------------- LINEMOD-style metrics (8f.3) */
+/* evaluation.py:340-411 (projection_2d[_sym], add_metric[_sym], cm_degree_5_metric), batched: pred / gt poses
+ * [N,3,4] f64 row-major [R|t], model [n_model,3] f64, K [9] f64 (needed for proj2d).  symmetric != 0 selects the
+ * nearest-point variants (ADD-S, projection_2d_sym: float32 search like nearest_neighborhood.cu, FP64 distances).
+ * Outputs [N] f64, any may be NULL: proj2d = mean 2-D reprojection distance (px), add = mean 3-D distance,
+ * cm = translation error * 100, deg = rotation error in degrees (NaN where trace < -1, like np.arccos).
+ * The pass flags of the reference (proj2d < threshold, add < diameter * percentage, cm < 5 and deg < 5) are
+ * comparisons on these values; the Python mirror applies them. */
+int epb_pose_metrics(const double* pred_rt34, const double* gt_rt34, int N, const double* model, int n_model,
+                     const double* K, int symmetric, double* proj2d, double* add, double* cm, double* deg,
+                     void* stream);
+/* lib/utils/extend_utils/extend_utils.py:40-61 find_nearest_point_idx (-> nearest_neighborhood.cu:48-121) on
+ * DEVICE buffers: ref_pts [pn1,dim], que_pts [pn2,dim] f32 (dim 2 or 3) -> idxs [pn2] i32, index of the nearest
+ * reference point (first minimum). */
+int epb_nearest_point_idx(const float* ref_pts, const float* que_pts, int32_t* idxs, int pn1, int pn2, int dim,
+                          void* stream);
 
 #ifdef __cplusplus
 }

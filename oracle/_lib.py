@@ -43,6 +43,10 @@ def ref_voting_lib(required=True):
     return _load(os.path.join(_HERE, "_ref", "libref_voting.so"), required)
 
 
+def ref_nearest_lib(required=True):
+    return _load(os.path.join(_HERE, "_ref", "libref_nearest.so"), required)
+
+
 def fptr(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
 

@@ -124,3 +124,37 @@ def vertex_hwvn2(vertex_nchw):
     """numpy form of vertex_layer_reshape (base_utils.py:311-316): [b,2vn,h,w] -> [b,h,w,vn,2]."""
     b, c, h, w = vertex_nchw.shape
     return np.ascontiguousarray(vertex_nchw.transpose(0, 2, 3, 1)).reshape(b, h, w, c // 2, 2)
+
+
+def make_pose_field(seed, n_images, size=256, vn=11, fg=0.25, noise_deg=2.0, model=None, mask_seed=None):
+    """Structured SPEED-like crops whose keypoints are CONSISTENT with a 3-D model (so that the pose solve
+    behind the voting has a consensus): the vn keypoints are the projections of the Tango model under a random
+    pose, scaled into the crop; field = unit vectors towards them + angular noise; mask = centred ellipse.
+    -> mask [n,s,s] u8, vertex NCHW [n,2vn,s,s] f32, model [vn,3], geom [n,3] = (bbox x, bbox y, rate) for the
+    un-crop of val.py:180 (ori = pred / rate + (x, y)), kcrop [n,vn,2] planted keypoints in crop pixels, and the
+    planted poses (rvec [n,3], t [n,3])."""
+    rng = np.random.default_rng(seed if mask_seed is None else mask_seed)
+    s = size
+    model = tango_model(vn, seed=9) if model is None else np.asarray(model)
+    ys, xs = np.mgrid[0:s, 0:s].astype(np.float32)
+    mask = np.zeros((n_images, s, s), np.uint8)
+    vertex = np.zeros((n_images, 2 * vn, s, s), np.float32)
+    kcrop = np.zeros((n_images, vn, 2))
+    geom = np.zeros((n_images, 3))
+    rvecs, ts = np.zeros((n_images, 3)), np.zeros((n_images, 3))
+    for i in range(n_images):
+        c = make_pose_case(seed * 100003 + i, vn, 0.0, 0, model=model)
+        lo, hi = c["p2d"].min(0), c["p2d"].max(0)
+        width = (hi - lo).max() * 1.6 + 8
+        org = (lo + hi) / 2 - width / 2
+        rate = s / width
+        kc = (c["p2d"] - org) * rate
+        kcrop[i] = kc
+        geom[i] = (org[0], org[1], rate)
+        rvecs[i], ts[i] = c["rvec"], c["t"]
+        mask[i] = ellipse_mask(s, s, fg, rng, jitter=0.03)
+        for v in range(vn):
+            ang = np.arctan2(kc[v, 1] - ys, kc[v, 0] - xs) + np.float32(np.deg2rad(noise_deg)) * rng.standard_normal((s, s), dtype=np.float32)
+            vertex[i, 2 * v] = np.cos(ang)
+            vertex[i, 2 * v + 1] = np.sin(ang)
+    return mask, vertex, model, geom, kcrop, rvecs, ts

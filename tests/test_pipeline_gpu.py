@@ -47,23 +47,36 @@ def test_heatmaps_to_pose_matches_oracle(cuda_dev):
 
 
 def test_vertex_to_pose_matches_oracle(cuda_dev):
+    """mask + field -> voting -> un-crop -> EPnP-RANSAC -> LM, keypoints AND poses against the oracle
+    (rotation 1e-3 deg, translation 1e-4 relative: north_star's tolerances)."""
+    import cv2
     from esa_pose_estimation_b200 import pipeline, ransac_voting_gpu as rv
+    from tests.synth import make_pose_field
     B, vn, S, hn = 4, 11, 96, 256
-    mask, vertex, kpts = make_vertex_field(61, B, S, S, vn, 0.35, noise_deg=1.5)
+    mask, vertex, model, geom, kcrop, _, _ = make_pose_field(61, B, S, vn, 0.35, noise_deg=1.5)
     vx = vertex_hwvn2(vertex)
-    model = tango_model(vn, seed=9)
     fn = ov.default_idxs_fn(3)
     idxs = np.zeros((B, 1, hn, vn, 2), np.int32)
     for bi in range(B):
         idxs[bi, 0] = fn(bi, 0, hn, vn, int((mask[bi] != 0).sum()))
-    K = np.array([[120.0, 0, 48], [0, 120.0, 48], [0, 0, 1]])
     out = pipeline.poses_from_vertex(torch.from_numpy(mask).to(cuda_dev),
                                      rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev)),
-                                     torch.from_numpy(model).to(cuda_dev), torch.from_numpy(K).to(cuda_dev),
-                                     round_hyp_num=hn, idxs=torch.from_numpy(idxs).to(cuda_dev))
+                                     torch.from_numpy(model).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev),
+                                     round_hyp_num=hn, idxs=torch.from_numpy(idxs).to(cuda_dev),
+                                     bbox_xy=torch.from_numpy(np.ascontiguousarray(geom[:, :2])).to(cuda_dev),
+                                     rate=torch.from_numpy(np.ascontiguousarray(geom[:, 2])).to(cuda_dev))
     k_o = ov.ransac_voting_layer_v3(mask, vx, hn, idxs_fn=fn)
     np.testing.assert_allclose(out["kpts"].cpu().numpy(), k_o, atol=1e-3)
-    assert out["pose7"].shape == (B, 7) and out["status"].shape == (B,)
+    assert np.abs(k_o - kcrop).max() < 2.0
+    assert out["pose7"].shape == (B, 7) and int(out["status"].abs().sum()) == 0
+    rt6 = out["rt6"].cpu().numpy()
+    for bi in range(B):
+        p2d = k_o[bi].astype(np.float64) * (1.0 / geom[bi, 2]) + geom[bi, :2]
+        rt = opose.pnp(model, p2d, ESA_K, cv2.SOLVEPNP_EPNP)
+        r_exp, _ = cv2.Rodrigues(rt[:, :3])
+        cam = opose.cpnp(model, p2d, ESA_K, np.concatenate([r_exp.reshape(3), rt[:, 3]]))
+        assert _ang(rodrigues(rt6[bi, :3]), rodrigues(cam[:3])) < 1e-3
+        assert np.linalg.norm(rt6[bi, 3:] - cam[3:]) / np.linalg.norm(cam[3:]) < 1e-4
 
 
 def test_smoke_entry(cuda_dev):

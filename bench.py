@@ -24,6 +24,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+TRAFFIC_PROFILE = "profiles/r2_vote_count_full.md"
 METRIC = "poses/sec (vector fields -> refined pose)"
 UNIT = "poses/s"
 
@@ -44,7 +45,18 @@ def parse():
                     help="batch pieces of the host-input pipeline (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side baseline (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (ncu launch lists of the device step)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the informational legs (other BASELINE configs, reference_gpu)")
     return ap.parse_args()
+
+
+def config_dict(a, world):
+    """The `config` object of BOTH arms (the driver compares them key by key)."""
+    return {"workload": workload_name(a), "batch_per_gpu": a.batch, "image": "%dx%d" % (a.size, a.size), "keypoints": a.vn,
+            "hypotheses": a.hn, "foreground_fraction": a.fg, "tn_mean": float(int(a.fg * a.size * a.size)),
+            "rng": "philox (torch layout); the torch generator is advanced by the data-independent upper bound "
+                   "(sync_rng=False: no host sync), not by what the reference would have consumed",
+            "l2_policy": "inputs larger than L2 (%.0f MB of vector field per step)" % (a.batch * 2 * a.vn * a.size * a.size * 4 / 1e6),
+            "parallelism": "images sharded by batch, 1 NCCL all_gather of poses" if world > 1 else "single GPU"}
 
 
 def workload_name(a):
@@ -124,7 +136,7 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_all / max(a.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": workload_name(a), "sample_images_per_step": per_step},
+            "data": "synthetic", "config": config_dict(a, max(a.gpus, 1)), "sample_images_per_step": per_step,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d images/step of the same workload through oracle/ (C voting restatement, "
                                        "cv2 EPnP-RANSAC, LM restatement), one process per core" % per_step},
@@ -226,6 +238,166 @@ class ClockSampler:
         return out
 
 
+def reference_gpu_voting(a, mask_d, vertex_d, n_images, reps=3):
+    """Informational: the REFERENCE's own CUDA kernels on the same data and box -- ransac_voting_kernel.cu:11-126
+    compiled unmodified for sm_100a (oracle/_ref/libref_voting.so) and driven like ransac_voting_gpu.py:523-598, one
+    image at a time: torch.nonzero / masked_select compaction, random_ indices, generate_hypothesis, the zeroed
+    [hn,vn,tn] byte tensor, voting_for_hypothesis, torch.sum, max, re-vote of the winners and the 2x2 normal
+    equations.  (Its pybind module cannot be built against torch 2.11; the launchers are called through ctypes on
+    raw device pointers, everything on the legacy default stream like the original.)  -> ms per image, or None."""
+    import ctypes
+    import torch
+    try:
+        from oracle import _lib as olib
+        lib = olib.ref_voting_lib(required=False)
+    except Exception:
+        lib = None
+    if lib is None:
+        return None
+    vp = ctypes.c_void_p
+    hn, vn, thresh = a.hn, a.vn, ctypes.c_float(0.999)
+
+    def one(bi):
+        cur_mask = mask_d[bi].byte()
+        coords = torch.nonzero(cur_mask).float()[:, [1, 0]].contiguous()
+        tn = coords.shape[0]
+        direct = vertex_d[bi].masked_select(cur_mask[:, :, None, None].bool()).view(tn, vn, 2).contiguous()
+        idxs = torch.zeros([hn, vn, 2], dtype=torch.int32, device=mask_d.device).random_(0, tn)
+        hyp = torch.zeros([hn, vn, 2], dtype=torch.float32, device=mask_d.device)
+        lib.ref_generate_hypothesis(vp(direct.data_ptr()), vp(coords.data_ptr()), vp(idxs.data_ptr()), vp(hyp.data_ptr()), tn, vn, hn)
+        inlier = torch.zeros([hn, vn, tn], dtype=torch.uint8, device=mask_d.device)
+        lib.ref_voting_for_hypothesis(vp(direct.data_ptr()), vp(coords.data_ptr()), vp(hyp.data_ptr()), vp(inlier.data_ptr()),
+                                      tn, vn, hn, thresh)
+        counts = torch.sum(inlier, 2)
+        _, win = torch.max(counts, 0)
+        win_pts = hyp[win, torch.arange(vn, device=hyp.device)].unsqueeze(0).contiguous()
+        inl2 = torch.zeros([1, vn, tn], dtype=torch.uint8, device=mask_d.device)
+        lib.ref_voting_for_hypothesis(vp(direct.data_ptr()), vp(coords.data_ptr()), vp(win_pts.data_ptr()), vp(inl2.data_ptr()),
+                                      tn, vn, 1, thresh)
+        w = inl2[0].float().t().unsqueeze(2)                                   # [tn,vn,1]
+        normal = torch.stack([direct[:, :, 1], -direct[:, :, 0]], 2) * w       # [tn,vn,2]
+        b_ = torch.sum(normal * coords.unsqueeze(1), 2, keepdim=True)          # [tn,vn,1]
+        ata = torch.einsum("tvi,tvj->vij", normal, normal)
+        atb = torch.einsum("tvi,tvk->vik", normal, b_)
+        return torch.linalg.solve(ata, atb)[:, :, 0]
+
+    for bi in range(min(2, n_images)):
+        one(bi)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for bi in range(n_images):
+            one(bi)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * n_images)
+
+
+def secondary_configs(a, world, rank, dev, timed, barrier):
+    """BASELINE.json configs 0, 2, 3, 4 (+ the pose solve under RANSAC pressure), measured with the same protocol as the
+    contract line: inputs resident in HBM, CUDA events, max over ranks.  configs 2 and 4 shard by image / pose across the
+    ranks (weak work split of a FIXED total: 3000 frames, 1e6 poses); 0 and 3 are single-GPU cases (rank 0, N = 1 only).
+    CPU legs (rank 0, N = 1, bounded samples) run the reference's per-frame loop through the oracle port."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs as bc
+    from esa_pose_estimation_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    peak = bc.PEAK
+
+    def try_(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:               # informational legs never take the contract line down
+            out[name] = {"failed": repr(e)}
+
+    # config[2]: 3000 frames of 11 x 384x384 heatmaps, sharded by frame, one call per rank, one all_gather of the poses
+    def c2():
+        from esa_pose_estimation_b200 import pipeline
+        n_total = 3000
+        s_, e_ = pipeline.shard_range(n_total, rank, world)
+        step, meta = bc.make_c3_step(e_ - s_, seed=2 + rank)
+
+        def full():
+            p = step()
+            return pipeline.gather_poses(p, n_total) if world > 1 else p
+        for _ in range(3):
+            full()
+        lib.epb_profile_enable(1)
+        steps = 5
+        ms = timed(full, steps) / steps
+        dec = _lib.c_double(0); n_ = _lib.c_int(0)
+        lib.epb_profile_read(5, dec, n_)
+        lib.epb_profile_enable(0)
+        per = dec.value / steps               # decode time of one pass (all its launches: the set goes through in pieces)
+        r = {"workload": "3000 frames x 11 x 384x384 heatmaps -> decode + EPnP-RANSAC + LM, %d frames per GPU, NCCL pose gather" % (e_ - s_),
+             "poses_per_s": n_total / (ms * 1e-3), "ms_per_pass": ms, "n_gpus": world,
+             "roofline": {"kernel": "decode_kernel", "bound": "hbm", "achieved": meta["heatmap_bytes"] / (per * 1e-3) / 1e9 if per > 0 else None,
+                          "peak": peak, "unit": "GB/s", "frac": meta["heatmap_bytes"] / (per * 1e-3) / 1e9 / peak if per > 0 else None,
+                          "decode_ms_per_pass": per, "launches_per_pass": n_.value / steps,
+                          "l2_policy": "inputs larger than L2 (%.1f GB per GPU)" % (meta["heatmap_bytes"] / 1e9)}}
+        del meta, step
+        torch.cuda.empty_cache()
+        return r
+    try_("config2_val_set_3000_frames", c2)
+
+    # config[4]: LM refinement sweep; the 1e6-pose point is sharded across the ranks
+    def c4():
+        sweep = []
+        for n_total in ((1000, 10000, 100000, 1000000) if world == 1 else (1000000,)):
+            per_rank = n_total // world
+            step, meta = bc.make_c5_step(per_rank, seed=5 + rank)
+            for _ in range(3):
+                step()
+            steps = 5 if n_total >= 100000 else 20
+            ms = timed(step, steps) / steps
+            sweep.append({"poses": per_rank * world, "ms": ms, "poses_per_s": per_rank * world / (ms * 1e-3)})
+            del step, meta
+        torch.cuda.empty_cache()
+        return {"workload": "batched LM refinement, 11-point model, start 2 deg / 2 % off, poses sharded across the GPUs",
+                "n_gpus": world, "sweep": sweep, "poses_per_s": sweep[-1]["poses_per_s"]}
+    try_("config4_lm_sweep", c4)
+
+    if world == 1:
+        try_("config0_single_frame", lambda: {k: v for k, v in bc.c1().items() if k != "config"})
+        try_("config3_768_fields_2048_hypotheses_covariance", lambda: {k: v for k, v in bc.c4().items() if k != "config"})
+        try_("pose_solve_under_ransac_pressure_64_frames", bc.pose_stress)
+        if not a.no_cpu_baseline:
+            def cpu_legs():
+                cores = os.cpu_count() or 1
+                v0, dt0, _ = bc.cpu_heatmap_path(max(16 * cores, 64), kp=11, s=128, cores=cores)
+                v2, dt2, _ = bc.cpu_heatmap_path(max(4 * cores, 32), kp=11, s=384, cores=cores)
+                v4, dt4, _ = bc.cpu_lm_sweep(20000, cores=cores)
+                return {"kind": "port", "cores": cores,
+                        "config0_frames_per_s": v0, "config2_frames_per_s": v2, "config4_poses_per_s": v4,
+                        "sample": "%d frames at 128x128 in %.1f s, %d frames at 384x384 in %.1f s, 20000 LM solves in %.1f s; "
+                                  "reference per-frame loop (val.py:151-228: numpy argmax + log-Taylor refine, cv2 EPnP-RANSAC, LM) "
+                                  "through oracle/, one process per core" % (max(16 * cores, 64), dt0, max(4 * cores, 32), dt2, dt4)}
+            try_("cpu_baseline", cpu_legs)
+    if world > 1:
+        barrier()
+    return out if rank == 0 else None
+
+
+def parse_traffic(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch in an ncu summary under profiles/ (tools/ncu_summary.py
+    format: `| `metric` | value | unit |`) -> bytes, or None."""
+    try:
+        tot, seen = 0.0, 0
+        for ln in open(path):
+            for key in ("dram__bytes_read.sum`", "dram__bytes_write.sum`"):
+                if key in ln and seen < 2:
+                    cells = [c.strip() for c in ln.split("|")]
+                    val, unit = float(cells[2]), cells[3].lower()
+                    tot += val * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+                    seen += 1
+        return int(tot) if seen == 2 else None
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -284,8 +456,10 @@ def run_ours(a):
     def step_e2e():
         # public API on HOST buffers: the mask is copied H2D, the pinned field is read in place over
         # PCIe by the gather kernel (foreground pixels only), the poses are copied D2H
+        # (host_inputs_ready: the pinned buffers were filled by the host before the loop and are never rewritten)
         out = pipeline.poses_from_vertex(mask_h, rv.vertex_layer_reshape(vertex_h), model_d, K_d, round_hyp_num=a.hn,
-                                         bbox_xy=bbox_d, rate=rate_d, sync_rng=False, chunks=a.e2e_chunks or None)
+                                         bbox_xy=bbox_d, rate=rate_d, sync_rng=False, chunks=a.e2e_chunks or None,
+                                         host_inputs_ready=True)
         p = pipeline.gather_poses(out["pose7"], a.batch * world) if world > 1 else out["pose7"]
         pose_h.copy_(p[rank * a.batch:(rank + 1) * a.batch] if world > 1 else p, non_blocking=True)
         return p
@@ -325,6 +499,18 @@ def run_ours(a):
     # 2 deg of direction noise at up to ~size px from the keypoint: the refined point lands within ~1 px at 256
     assert kerr < 1.5 * max(a.size, 256) / 256.0, "voting did not recover the planted keypoints (max err %.3f px)" % kerr
 
+    if world > 1:
+        # the gathered [N*B,7] block must hold every rank's poses in image order: this rank's slice == its local poses
+        out_chk = pipeline.poses_from_vertex(mask_d, rv.vertex_layer_reshape(vertex_d), model_d, K_d, round_hyp_num=a.hn,
+                                             bbox_xy=bbox_d, rate=rate_d, sync_rng=False)
+        g_chk = pipeline.gather_poses(out_chk["pose7"], a.batch * world)
+        assert torch.equal(g_chk[rank * a.batch:(rank + 1) * a.batch], out_chk["pose7"]), "NCCL gather: local slice differs"
+        cs = g_chk.double().sum(1)
+        ref_cs = [torch.empty_like(cs) for _ in range(world)]
+        dist.all_gather(ref_cs, cs)
+        assert all(torch.equal(ref_cs[0], r_) for r_ in ref_cs), "NCCL gather: ranks hold different gathered poses"
+        barrier()
+
     lib.epb_profile_enable(1)
     launches0 = lib.epb_launch_count()
     t_dev0 = time.time()
@@ -357,6 +543,15 @@ def run_ours(a):
     if sampler:
         sampler.stop()
         clocks, clocks_e2e = sampler.region(t_dev0, t_dev1), sampler.region(t_e0, t_e1)
+
+    # --- the other BASELINE.json configurations (informational; `value` above is the contract line)
+    configs = None if a.no_configs else secondary_configs(a, world, rank, dev, timed, barrier)
+    ref_gpu_ms = None
+    if rank == 0 and world == 1 and not a.no_configs:
+        try:
+            ref_gpu_ms = reference_gpu_voting(a, mask_d, rv.vertex_layer_reshape(vertex_d), min(a.batch, 8))
+        except Exception as e:           # informational leg: never takes the contract line down
+            ref_gpu_ms = "failed: %r" % (e,)
 
     if rank != 0:
         if world > 1:
@@ -394,10 +589,9 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "batch_per_gpu": a.batch, "tn_mean": tn, "rng": "philox (torch layout)",
-                   "l2_policy": "inputs larger than L2 (%.0f MB of vector field per step)" % (vertex_h.numel() * 4 / 1e6),
-                   "parallelism": "images sharded by batch, 1 NCCL all_gather of poses" if world > 1 else "single GPU"},
+        "config": config_dict(a, world), "tn_mean_measured": tn,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "pipeline.poses_from_vertex(pinned host mask, pinned host field, ..., host_inputs_ready=True) + pose D2H",
                 "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes, "clocks": clocks_e2e, "host_numa_binding": numa,
                 "transfer": "mask cudaMemcpyAsync from pinned memory; field read zero-copy from pinned memory by the "
                             "compaction kernel (foreground pixel groups only); poses D2H into pinned memory"},
@@ -407,8 +601,9 @@ def run_ours(a):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the default workload, from the
                      # ncu --set full capture summarised in profiles/r1_vote_count_full.md (100.9 MB + 5.4 MB): well
                      # BELOW the algorithmic bytes, because only the foreground of the field is ever touched
-                     "traffic": 106282752 if (a.batch, a.size, a.vn, a.hn, a.fg) == (64, 256, 11, 512, 0.25) else None,
-                     "traffic_source": "profiles/r1_vote_count_full.md", "peak_source": peak_src,
+                     "traffic": parse_traffic(os.path.join(ROOT, TRAFFIC_PROFILE)) if (a.batch, a.size, a.vn, a.hn, a.fg) == (64, 256, 11, 512, 0.25) else None,
+                     "traffic_source": TRAFFIC_PROFILE + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_s * 1e3,
                      "share_of_step": (vote_ms / a.steps) / step_ms if step_ms > 0 else None,
                      "note": "FP32-ALU-bound at this foreground (SURVEY 8d): see alu",
@@ -426,6 +621,15 @@ def run_ours(a):
         "value_batches_in_flight": {"caller_streams": n_streams, "value": poses_per_step * a.steps / (ms_streams * 1e-3),
                                     "ms_per_step": ms_streams / a.steps, "unit": UNIT},
     }
+    if configs is not None:
+        line["configs"] = configs
+    voting_ms = sum(prof[k][0] for k in ("compaction", "hypothesis", "vote_count", "winner_refine")) / a.steps
+    line["reference_gpu"] = {
+        "what": "the reference's own voting kernels (ransac_voting_kernel.cu compiled unmodified for sm_100a) driven like "
+                "ransac_voting_gpu.py:523-598 (per image: torch compaction, random_, generate_hypothesis, [hn,vn,tn] byte tensor, "
+                "voting_for_hypothesis, torch.sum, max, re-vote, normal equations), same data, same GPU; keypoints only (no PnP / LM)",
+        "ms_per_image": ref_gpu_ms, "ours_voting_ms_per_image": voting_ms / a.batch,
+        "speedup_voting": (ref_gpu_ms / (voting_ms / a.batch)) if isinstance(ref_gpu_ms, float) and voting_ms > 0 else None}
     if a.no_e2e:                              # profiling runs: keep the line valid JSON (no NaN)
         line["e2e"].update(value=None, ms_per_step=None)
         line["value_batches_in_flight"].update(value=None, ms_per_step=None)

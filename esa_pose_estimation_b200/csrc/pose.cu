@@ -360,7 +360,10 @@ __device__ void compute_r_and_t3(const WarpScratch& ws, const double be[4], cons
 }
 
 // EPnP over the lanes flagged `active` (n = popcount >= 4).  All lanes return the same pose.
-__device__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int first_lane,
+// (one out-of-line copy: the RANSAC candidates, the speculative all-point solve and the final solve over the
+// consensus set share it, so the W = 2 / 4 / 8 instantiations of the kernels execute the SAME machine code and
+// return bit-identical poses whatever the batch size; it also takes two inlined copies out of the instruction cache)
+__device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int first_lane,
                           const double pw_in[3], double u, double v, const Cam& cam, PoseRT& best) {
   double pw[3] = {active ? pw_in[0] : 0.0, active ? pw_in[1] : 0.0, active ? pw_in[2] : 0.0};
   // control points: centroid + PCA axes (OpenCV SVD sign convention)
@@ -538,32 +541,43 @@ __device__ int ransac_update_num_iters(double p, double ep, int model_points, in
 
 // cv2.solvePnPRansac(flags=EPNP) restated (oracle/epnp_port.py solve_pnp_ransac_epnp).
 // pw/u/v are this lane's correspondence (already rounded to float32 by the caller, as
-// OpenCV converts its inputs to CV_32F).  Returns status; all lanes hold the same result.
+// OpenCV converts its inputs to CV_32F).  Returns status; all lanes of warp 0 hold the result.
 //
-// Two warps per image (CTA = 64 threads).  OpenCV ends with one EPnP over the consensus set; on clean
-// frames that set is "all points" and is known only after the first 5-point sample has been solved and
-// scored.  Warp 1 (role 1) therefore solves EPnP over ALL points speculatively while warp 0 (role 0)
-// runs the RANSAC loop; when the consensus turns out to be everything -- the common case -- warp 0 takes
-// warp 1's result instead of starting the second eigen-solve, which removes ~40 % of the latency of this
-// latency-bound kernel.  Otherwise nothing changes (the speculative result is dropped).  Exactly one
-// __syncthreads() is executed on every path of both roles.
+// W warps per image (CTA = 32 W threads), W in {2, 4, 8}.  OpenCV's loop is sequential -- iteration k draws its
+// 5-point sample from cv::RNG, solves, scores, and a better consensus shortens `niters` -- but the SAMPLES do not
+// depend on the data: every warp runs the same generator and knows the sample of every iteration.  So the
+// iterations are evaluated W at a time, one per warp, and the sequential bookkeeping (strictly-better consensus,
+// niters update, stop) is then REPLAYED in iteration order over the W results by every warp identically.  A result
+// beyond the shortened niters is ignored, exactly as if it had never been computed: the consensus set equals
+// OpenCV's for every input, while one outlier in 11 points costs one round instead of ~5 serial solves and the
+// no-consensus case ceil(100 / W) rounds instead of 100.
+// Round 0 keeps the round-1 trick: OpenCV ends with one EPnP over the consensus set; on clean frames that set is
+// "all points" and is known only after the first sample has been solved and scored, so warp 1 solves EPnP over
+// ALL points speculatively during round 0 (the other warps take iterations 0, 1, ..., W - 2) and warp 0 takes
+// its result when the consensus turns out to be everything.  Every warp executes the same barriers.
+struct RansacShared {
+  PoseRT spec;          // EPnP over all points (warp 1, round 0)
+  int cnt[8];           // per slot: consensus size of the candidate, -1 = not evaluated / non-finite model
+  unsigned mask[8];
+};
+
+template <int W>
 __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw[3], double u, double v,
                                const Cam& cam, double reproj_err, int max_iters, double confidence,
-                               PoseRT& out, unsigned& inlier_mask, int role, PoseRT* s_spec) {
+                               PoseRT& out, unsigned& inlier_mask, int warp, RansacShared* sh) {
+  static_assert(W >= 2 && W <= 8, "slots of RansacShared");
   const int model_points = 5;
   inlier_mask = 0;
-  if (n < model_points) return EPB_POSE_TOO_FEW;
+  if (n < model_points) return EPB_POSE_TOO_FEW;   // (uniform over the CTA: no barrier has been executed)
   const unsigned all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-  if (role == 1) {
-    PoseRT sp;
-    epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
-    if (lane == 0) *s_spec = sp;
+  if (n == model_points) {       // the minimal sample is the whole set: OpenCV solves it once
+    if (warp == 1) {
+      PoseRT sp;
+      epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
+      if (lane == 0) sh->spec = sp;
+    }
     __syncthreads();
-    return EPB_POSE_OK;
-  }
-  if (n == model_points) {
-    __syncthreads();
-    out = *s_spec;
+    out = sh->spec;
     inlier_mask = all;
     return EPB_POSE_OK;
   }
@@ -571,42 +585,76 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   int niters = max_iters;
   unsigned best_mask = 0;
   int best_count = 0;
-  bool synced = false;
   const float thr2 = (float)(reproj_err * reproj_err);
-  for (int it = 0; it < niters; ++it) {
-    int idx[5];
-    unsigned m = 0;
+  int it0 = 0;                                       // iterations replayed so far
+  for (int round = 0; it0 < niters; ++round) {
+    // Round 0 is what a clean frame pays: at most four warps work in it (one per scheduler: the critical warps 0
+    // and 1 do not share issue slots), warp 1 on the speculative solve; warps 4.. join from round 1 on.
+    constexpr int W0 = W < 4 ? W : 4;
+    const int slots = round == 0 ? W0 - 1 : W;
+    const int my_slot = round == 0 ? (warp == 0 ? 0 : warp - 1) : warp;
+    const bool speculative = round == 0 && warp == 1;
+    const bool idle = round == 0 && warp >= W0;
+    // advance the generator through the round; keep the sample of this warp's iteration
+    int idx0 = 0;
+    unsigned my_m = 0;
+    for (int sl = 0; sl < slots; ++sl) {
+      unsigned m = 0;
+      int first = 0;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      int k = rng.uniform(0, n);
-      while (m & (1u << k)) k = rng.uniform(0, n);
-      idx[i] = k; m |= 1u << k;
+      for (int i = 0; i < 5; ++i) {
+        int k = rng.uniform(0, n);
+        while (m & (1u << k)) k = rng.uniform(0, n);
+        if (i == 0) first = k;
+        m |= 1u << k;
+      }
+      if (sl == my_slot && !speculative) { my_m = m; idx0 = first; }
     }
-    PoseRT cur;
-    epnp_core(ws, lane, (m >> lane) & 1u, 5, idx[0], pw, u, v, cam, cur);
-    bool finite = true;
+    if (speculative) {
+      PoseRT sp;
+      epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
+      if (lane == 0) sh->spec = sp;
+    } else {
+      int cnt = -1;
+      unsigned gm = 0;
+      if (!idle && it0 + my_slot < niters) {
+        PoseRT cur;
+        epnp_core(ws, lane, (my_m >> lane) & 1u, 5, idx0, pw, u, v, cam, cur);
+        bool finite = true;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) finite = finite && isfinite(cur.R[i]);
+        for (int i = 0; i < 9; ++i) finite = finite && isfinite(cur.R[i]);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) finite = finite && isfinite(cur.t[i]);
-    if (finite) {
-      const double xc = cur.R[0] * pw[0] + cur.R[1] * pw[1] + cur.R[2] * pw[2] + cur.t[0];
-      const double yc = cur.R[3] * pw[0] + cur.R[4] * pw[1] + cur.R[5] * pw[2] + cur.t[1];
-      const double zc = cur.R[6] * pw[0] + cur.R[7] * pw[1] + cur.R[8] * pw[2] + cur.t[2];
-      const double du = u - (cam.uc + cam.fu * xc / zc), dv = v - (cam.vc + cam.fv * yc / zc);
-      const bool good = lane < n && ((float)(du * du + dv * dv) <= thr2);
-      const unsigned gm = __ballot_sync(FULL, good);
-      const int cnt = __popc(gm);
+        for (int i = 0; i < 3; ++i) finite = finite && isfinite(cur.t[i]);
+        if (finite) {
+          const double xc = cur.R[0] * pw[0] + cur.R[1] * pw[1] + cur.R[2] * pw[2] + cur.t[0];
+          const double yc = cur.R[3] * pw[0] + cur.R[4] * pw[1] + cur.R[5] * pw[2] + cur.t[1];
+          const double zc = cur.R[6] * pw[0] + cur.R[7] * pw[1] + cur.R[8] * pw[2] + cur.t[2];
+          const double du = u - (cam.uc + cam.fu * xc / zc), dv = v - (cam.vc + cam.fv * yc / zc);
+          const bool good = lane < n && ((float)(du * du + dv * dv) <= thr2);
+          gm = __ballot_sync(FULL, good);
+          cnt = __popc(gm);
+        }
+      }
+      if (lane == 0 && !idle) { sh->cnt[my_slot] = cnt; sh->mask[my_slot] = gm; }
+    }
+    __syncthreads();
+    // replay OpenCV's sequential bookkeeping over the round (identical in every warp)
+    for (int sl = 0; sl < slots && it0 + sl < niters; ++sl) {
+      const int cnt = sh->cnt[sl];
       if (cnt > max(best_count, model_points - 1)) {
-        best_mask = gm; best_count = cnt;
+        best_mask = sh->mask[sl]; best_count = cnt;
         niters = ransac_update_num_iters(confidence, (double)(n - cnt) / n, model_points, niters);
       }
     }
-    if (!synced) { __syncthreads(); synced = true; }
+    it0 += slots;
+    __syncthreads();      // the slots are rewritten by the next round
   }
-  if (!synced) __syncthreads();
+  if (max_iters <= 0) {   // (no round ran: the speculative result does not exist either)
+    return EPB_POSE_FAILED;
+  }
   if (best_mask == 0) return EPB_POSE_FAILED;
-  if (best_mask == all) out = *s_spec;   // == epnp_core over all points, first_lane 0
+  if (warp != 0) return EPB_POSE_OK;                 // only warp 0 carries the pose on
+  if (best_mask == all) out = sh->spec;              // == epnp_core over all points, first_lane 0
   else epnp_core(ws, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
   inlier_mask = best_mask;
   return EPB_POSE_OK;
@@ -855,14 +903,15 @@ __device__ __forceinline__ Cam load_cam(const double* K, int batched, int img) {
 }
 __device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
 
-__global__ void __launch_bounds__(64)
+template <int W>
+__global__ void __launch_bounds__(32 * W)
 pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __restrict__ p2d,
            const double* __restrict__ K, int K_batched, const int32_t* __restrict__ npts, int B,
            int n_max, double reproj_err, int max_iters, double confidence, double* __restrict__ rt34,
            unsigned long long* __restrict__ inlier_mask, int32_t* __restrict__ status) {
-  __shared__ WarpScratch scratch[2];
-  __shared__ PoseRT s_spec;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp = role (0 RANSAC, 1 speculative)
+  __shared__ WarpScratch scratch[W];
+  __shared__ RansacShared s_ransac;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0 carries the result; all evaluate candidates
   const int img = blockIdx.x;
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
@@ -878,8 +927,8 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
   const Cam cam = load_cam(K, K_batched, img);
   PoseRT out;
   unsigned mask = 0;
-  const int st = pnp_ransac_epnp(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
-                                 &s_spec);
+  const int st = pnp_ransac_epnp<W>(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
+                                    &s_ransac);
   if (warp == 0 && lane == 0) {
     double* o = rt34 + (size_t)img * 12;
     if (st == EPB_POSE_OK) {
@@ -1156,17 +1205,18 @@ __global__ void cov_to_weights_kernel(const float* __restrict__ cov, int n, int 
 }
 
 // val.py:172-228 for a batch: one warp per frame, lane k <-> keypoint k (K <= 32)
-__global__ void __launch_bounds__(64)
+template <int W>
+__global__ void __launch_bounds__(32 * W)
 pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ maxvals,
                      const double* __restrict__ bbox_xy, const double* __restrict__ rate,
                      const double* __restrict__ p3d_model, const double* __restrict__ Kmat, int B, int K,
                      int min_k, double sel_thresh, int weighted, float* __restrict__ pose7,
                      double* __restrict__ rt6_out, double* __restrict__ epnp_rt34,
                      int32_t* __restrict__ status) {
-  __shared__ WarpScratch scratch[2];
-  __shared__ PoseRT s_spec;
-  __shared__ double s_pts[2][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order (one copy per role)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp = role (0 RANSAC + LM, 1 speculative EPnP)
+  __shared__ WarpScratch scratch[W];
+  __shared__ RansacShared s_ransac;
+  __shared__ double s_pts[W][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order (one copy per warp: no barrier needed)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0: RANSAC bookkeeping + LM; all: candidates
   const int img = blockIdx.x;
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
@@ -1175,10 +1225,14 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   const float mv = have ? maxvals[(size_t)img * K + lane] : -INFINITY;
   int large_k = __popc(__ballot_sync(FULL, have && (double)mv > sel_thresh));
   large_k = min(max(large_k, min_k), K);
+  // heapq.nlargest order: by maxval, ties keep the lower index.  NaN compares false with everything, which would
+  // give every NaN lane rank 0: it ranks as -inf instead (a NaN keypoint that is still selected makes every
+  // candidate model non-finite, i.e. a clean EPB_POSE_FAILED with a NaN pose)
+  const float mk = (mv == mv) ? mv : -INFINITY;
   int rank = 0;
   for (int j = 0; j < K; ++j) {
-    const float mj = __shfl_sync(FULL, mv, j);
-    rank += (mj > mv) || (mj == mv && j < lane);
+    const float mj = __shfl_sync(FULL, mk, j);
+    rank += (mj > mk) || (mj == mk && j < lane);
   }
   // --- un-crop (val.py:180): float32 pred * (1/rate) + (x, y), in float64
   if (have) {
@@ -1202,9 +1256,9 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   const double pwf[3] = {round_f32(pt[0]), round_f32(pt[1]), round_f32(pt[2])};
   PoseRT init;
   unsigned mask = 0;
-  const int st = pnp_ransac_epnp(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask, warp,
-                                 &s_spec);
-  if (warp == 1) return;
+  const int st = pnp_ransac_epnp<W>(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask, warp,
+                                    &s_ransac);
+  if (warp != 0) return;
   double x[6];
   if (st == EPB_POSE_OK) {
     matrix_to_rodrigues(init.R, x);
@@ -1214,7 +1268,9 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
       for (int i = 0; i < 3; ++i) { o[4 * i] = init.R[3 * i]; o[4 * i + 1] = init.R[3 * i + 1]; o[4 * i + 2] = init.R[3 * i + 2]; o[4 * i + 3] = init.t[i]; }
     }
     // --- cpnp_m: LM with maxval weights on the unrounded float64 correspondences
-    const double ww = weighted ? w : 1.0;
+    // cpnp_m's weighting is not recoverable (binary and source absent): maxval itself (1, the documented
+    // assumption), sqrt(maxval) (2) or unit weights (0 = cpnp)
+    const double ww = weighted == 1 ? w : (weighted == 2 ? sqrt(fmax(w, 0.0)) : 1.0);
     lm_solve(x, pt, u, v, ww, 0.0, ww, cam, active, nullptr, nullptr);
   } else {
     for (int k = 0; k < 6; ++k) x[k] = NAN;
@@ -1264,9 +1320,18 @@ static inline void pose_launch_shape(int B, int* grid, int* block) {
   *grid = (B + warps - 1) / warps;
 }
 
+// RANSAC candidates evaluated side by side per image: the kernel is one long serial FP64 chain per warp (255
+// registers), so extra warps are free while SMs are idle and cost throughput once the batch fills the machine
+static inline int ransac_warps(int B) {
+  const int sms = device_sm_count();
+  return B <= sms ? 8 : (B <= 2 * sms ? 4 : 2);
+}
+
 static void pose_kernel_attributes() {
-  prefer_max_shared(pnp_kernel); prefer_max_shared(lm_kernel); prefer_max_shared(pose_pack_kernel);
-  prefer_max_shared(rt34_to_rt6_kernel); prefer_max_shared(cov_to_weights_kernel); prefer_max_shared(pose_pipeline_kernel);
+  prefer_max_shared(pnp_kernel<2>); prefer_max_shared(pnp_kernel<4>); prefer_max_shared(pnp_kernel<8>);
+  prefer_max_shared(lm_kernel); prefer_max_shared(pose_pack_kernel);
+  prefer_max_shared(rt34_to_rt6_kernel); prefer_max_shared(cov_to_weights_kernel);
+  prefer_max_shared(pose_pipeline_kernel<2>); prefer_max_shared(pose_pipeline_kernel<4>); prefer_max_shared(pose_pipeline_kernel<8>);
   prefer_max_shared(esa_score_kernel);
   cudaGetLastError();
 }
@@ -1278,10 +1343,13 @@ extern "C" int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const dou
   EPB_INIT_ONCE_PER_DEVICE(pose_kernel_attributes);
   if (!p3d || !p2d || !K || !rt34 || B < 0 || n_max <= 0 || n_max > 32 || max_iters < 0) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
-  const int grid = B, block = 64;   // two warps per image: RANSAC + speculative all-point EPnP
-  pnp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-      p3d, p3d_batched, p2d, K, K_batched, npts, B, n_max, reproj_err, max_iters, confidence, rt34,
-      inlier_mask, status);
+  // W warps per image evaluate RANSAC candidates side by side (pnp_ransac_epnp): 8 while every image still gets
+  // an SM of its own, fewer when the batch has to share them
+  const int W = ransac_warps(B);
+#define EPB_PNP_LAUNCH(WW) pnp_kernel<WW><<<B, 32 * WW, 0, (cudaStream_t)stream>>>(                         \
+      p3d, p3d_batched, p2d, K, K_batched, npts, B, n_max, reproj_err, max_iters, confidence, rt34, inlier_mask, status)
+  if (W == 8) EPB_PNP_LAUNCH(8); else if (W == 4) EPB_PNP_LAUNCH(4); else EPB_PNP_LAUNCH(2);
+#undef EPB_PNP_LAUNCH
   return check_launch();
 }
 
@@ -1342,10 +1410,11 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
   if (!pose7 && !rt6) return EPB_ERR_INVALID;
   if (B == 0) return EPB_OK;
   ProfScope ps(PROF_POSE, (cudaStream_t)stream);
-  const int grid = B, block = 64;
-  pose_pipeline_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(
-      preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6,
-      epnp_rt34, status);
+  const int W = ransac_warps(B);
+#define EPB_POSE_LAUNCH(WW) pose_pipeline_kernel<WW><<<B, 32 * WW, 0, (cudaStream_t)stream>>>(                   \
+      preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6, epnp_rt34, status)
+  if (W == 8) EPB_POSE_LAUNCH(8); else if (W == 4) EPB_POSE_LAUNCH(4); else EPB_POSE_LAUNCH(2);
+#undef EPB_POSE_LAUNCH
   return check_launch();
 }
 

@@ -80,7 +80,7 @@ constexpr int VM_REC_STAGES = 3;
 constexpr int VM_RAW_STAGES = 4;
 constexpr int VM_THREADS = VM_WARPS * 32;        // 256: two CTAs per SM own the whole register file at 128 registers
 #ifndef VM_PREDICATED
-#define VM_PREDICATED 1
+#define VM_PREDICATED 0
 #endif
 constexpr int VM_QCAP = 2048;                    // deferred undecided pairs per work unit
 

@@ -611,7 +611,7 @@ __host__ inline VoteConsts vote_consts(float thresh, int H, int W) {
 }
 
 constexpr int VOTE_QCAP = 1024;  // deferred undecided pairs per work unit (overflow is resolved in line)
-constexpr int VOTE_RAW_STAGES = 2;
+constexpr int VOTE_RAW_STAGES = 1;   // consumed in the middle of the previous tile, refilled after its barrier
 struct VoteSmem {
   float4 f[2][VOTE_TILE];  // A1 A2 B1 B2
   float2 g[2][VOTE_TILE];  // A3 B3
@@ -683,27 +683,31 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
 
     const uint32_t* fp = ws.fgpix + (size_t)b * ws.cap;
     const float2* dir = ws.direct + ((size_t)b * p.vn + v) * ws.cap;
-    // Tiles arrive by TMA: thread 0 issues two bulk copies per tile (cp.async.bulk global -> shared, completion
+    // Tiles 1.. arrive by TMA: thread 0 issues two bulk copies per tile (cp.async.bulk global -> shared, completion
     // counted in bytes on an mbarrier), always whole tiles -- the workspace rows are padded to VOTE_TILE pixels, the
     // records beyond t_end are marked as padding by index.  No register staging: a tile is in flight for a whole
-    // tile of compute (~11 k cycles) before anybody looks at it.
+    // tile of compute (~11 k cycles) before anybody looks at it.  Tile 0 is loaded directly (a TMA round trip at the
+    // start of every 25 us work unit cost 3 % of the kernel).
     const int ntiles = (t_end - t_begin + VOTE_TILE - 1) / VOTE_TILE;
-    auto tma_issue = [&](int i) {   // thread 0
-      const int rs = i % VOTE_RAW_STAGES;
+    auto tma_issue = [&](int i) {   // thread 0; tile i >= 1 goes to raw stage (i - 1) % VOTE_RAW_STAGES
+      const int rs = (i - 1) % VOTE_RAW_STAGES;
       mbar_expect_tx(&sm.raw_full[rs], VOTE_TILE * 12);
       bulk_g2s(sm.raw_dir[rs], dir + t_begin + (size_t)i * VOTE_TILE, VOTE_TILE * 8, &sm.raw_full[rs]);
       bulk_g2s(sm.raw_pix[rs], fp + t_begin + (size_t)i * VOTE_TILE, VOTE_TILE * 4, &sm.raw_full[rs]);
     };
 
-    // records of tile i (raw stage i % VOTE_RAW_STAGES) -> record buffer `buf`
+    // records of tile i -> record buffer `buf` (tile 0 from global memory, the others from their TMA raw stage)
     auto stage = [&](int i, int buf) {
-      const int rs = i % VOTE_RAW_STAGES;
-      mbar_wait(&sm.raw_full[rs], (unsigned)(i / VOTE_RAW_STAGES) & 1u);
+      const int rs = (i - 1) % VOTE_RAW_STAGES;
+      if (i > 0) mbar_wait(&sm.raw_full[rs], (unsigned)((i - 1) / VOTE_RAW_STAGES) & 1u);
 #pragma unroll
       for (int k = 0; k < PER_THREAD; ++k) {
         const int slot_in = k * VOTE_THREADS + threadIdx.x;
-        const uint32_t q = (t_begin + i * VOTE_TILE + slot_in < t_end) ? sm.raw_pix[rs][slot_in] : 0xffffffffu;
-        const float2 dn = sm.raw_dir[rs][slot_in];
+        const int t = t_begin + i * VOTE_TILE + slot_in;
+        uint32_t q = 0xffffffffu;
+        float2 dn = make_float2(0.f, 0.f);
+        if (i == 0) { if (t < t_end) { q = __ldg(fp + t); dn = __ldg(dir + t); } }
+        else { if (t < t_end) q = sm.raw_pix[rs][slot_in]; dn = sm.raw_dir[rs][slot_in]; }
         const float cx = (float)(q & 0xffff), cy = (float)(q >> 16);
         const float nx = dn.x, ny = dn.y;
         const float s1 = __fmaf_rn(nx, nx, __fmul_rn(ny, ny));
@@ -778,13 +782,10 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
 #pragma unroll
       for (int i = 0; i < VOTE_RAW_STAGES; ++i) mbar_init(&sm.raw_full[i], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      for (int i = 0; i < min(VOTE_RAW_STAGES, ntiles); ++i) tma_issue(i);
+      for (int i = 1; i <= min(VOTE_RAW_STAGES, ntiles - 1); ++i) tma_issue(i);
     }
-    __syncthreads();
     stage(0, 0);
     __syncthreads();
-    // raw stage 0 is free again (everybody has staged tile 0)
-    if (threadIdx.x == 0 && VOTE_RAW_STAGES < ntiles) tma_issue(VOTE_RAW_STAGES);
     for (int t0 = t_begin, ti = 0; t0 < t_end; t0 += VOTE_TILE, ++ti) {
       const bool more = t0 + VOTE_TILE < t_end;
       const int nrec = min(VOTE_TILE, t_end - t0);
@@ -795,8 +796,12 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
       const int ntrip = (nrec + RECS - 1) / RECS;
       const float4* frp = fr;
       const float2* grp = gr;
+      // The records of the NEXT tile are built in the middle of this one (its raw stage landed a whole tile ago): the
+      // mbarrier check, the raw loads and the record arithmetic of a warp then run under the trips of the other
+      // warps instead of in front of the end-of-tile barrier, where the whole CTA would wait for them.
+      auto trips = [&](int it_begin, int it_end) {
 #pragma unroll 1
-      for (int it = 0; it < ntrip; ++it, frp += RECS, grp += RECS) {
+      for (int it = it_begin; it < it_end; ++it, frp += RECS, grp += RECS) {
         const int i = it * RECS;
         float m[RECS][R], w[RECS][R];
         bool ambj[RECS], amb = false;
@@ -817,10 +822,13 @@ vote_count_kernel(epb_voting_params p, Workspace ws, VoteConsts vc,
 #pragma unroll
           for (int r = 0; r < R; ++r) neg[r] += __float_as_uint(m[j][r]) >> 31;
       }
+      };
+      trips(0, ntrip / 2);
       if (more) stage(ti + 1, buf ^ 1);
+      trips(ntrip / 2, ntrip);
       __syncthreads();
       // everybody has staged tile ti + 1: its raw stage takes the tile VOTE_RAW_STAGES further on
-      if (threadIdx.x == 0 && ti + 1 + VOTE_RAW_STAGES < ntiles) tma_issue(ti + 1 + VOTE_RAW_STAGES);
+      if (threadIdx.x == 0 && more && ti + 1 + VOTE_RAW_STAGES < ntiles) tma_issue(ti + 1 + VOTE_RAW_STAGES);
       buf ^= 1;
     }
 
@@ -1366,14 +1374,10 @@ static void voting_kernel_attributes() {
   prefer_max_shared(mask_count_kernel); prefer_max_shared(mask_scan_kernel); prefer_max_shared(rng_offsets_kernel);
   prefer_max_shared(mask_scatter_kernel<true>); prefer_max_shared(mask_scatter_kernel<false>);
   prefer_max_shared(field_gather_kernel); prefer_max_shared(hypothesis_kernel); prefer_max_shared(vote_items_kernel);
-  // vote_count: 8 CTAs x 22.6 KB (records + TMA raw stages + queue) need 181 KB of shared memory per SM
-  cudaFuncSetAttribute(reinterpret_cast<const void*>(vote_count_kernel<2>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(reinterpret_cast<const void*>(vote_count_kernel<4>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(reinterpret_cast<const void*>(vote_count_kernel<8>), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  prefer_max_shared(vote_exact_kernel);
-#ifdef EPB_TUNING
-  prefer_max_shared(vote_mma_kernel);
-#endif
+  // vote_count: 19.6 KB per CTA (records + one TMA raw stage + queue).  The library-wide carve-out (60 %, common.cuh)
+  // holds 6 of them per SM; asking for more (75 %, 100 %: 8 CTAs) measured the same device-resident time (1.75 ms)
+  // and a slower host pipeline (24.8 k vs 26.3 k poses/s end to end), where the gather and pose kernels share the SMs
+  prefer_max_shared(vote_count_kernel<2>); prefer_max_shared(vote_count_kernel<4>); prefer_max_shared(vote_count_kernel<8>);
   prefer_max_shared(counts_export_kernel); prefer_max_shared(winner_refine_kernel); prefer_max_shared(distribution_kernel);
   prefer_max_shared(motion_mean_kernel);
   prefer_max_shared(generate_hypothesis_kernel); prefer_max_shared(voting_for_hypothesis_kernel);
@@ -1385,7 +1389,8 @@ static int g_vote_r_large = 4;
 
 // Work units of the vote kernel: (item of <= item_px voting pixels, keypoint, hypothesis chunk), listed on the
 // device (vote_items_kernel) so that ragged batches balance without a host sync; CTAs beyond the list exit at once.
-static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, const VoteConsts& vc, cudaStream_t s) {
+static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, const VoteConsts& vc, bool headroom,
+                            cudaStream_t s) {
   const int HN = p.hn * p.rounds;
   int R = HN <= 256 ? 2 : (HN <= 512 ? 4 : g_vote_r_large);
   { const int forced = tuning_int("EPB_VOTE_R", 0); if (forced == 2 || forced == 4 || forced == 8) R = forced; }
@@ -1400,9 +1405,22 @@ static int launch_vote_ffma(const epb_voting_params& p, const Workspace& ws, con
   vote_items_kernel<<<1, 256, 0, s>>>(p.B, item_px, ws);
   EPB_RETURN_IF(check_launch());
   EPB_RETURN_IF(check_api(cudaMemsetAsync(ws.counts, 0, (size_t)p.B * p.vn * HN * 4, s)));
-  if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
-  else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
-  else vote_count_kernel<8><<<grid, VOTE_THREADS, 0, s>>>(p, ws, vc, item_px, chunks);
+  // Split runs (host pipeline) overlap this kernel with the gather stage of the next batch chunk on a high-priority
+  // stream.  Its small kernels can only start when an SM has registers to spare, so the vote CTAs are held two
+  // below full occupancy there (unused dynamic shared memory is the occupancy knob; measured in round 1: gather
+  // 0.75 -> 0.58 ms per chunk under a concurrent vote, vote 0.68 -> 0.61 ms).  Only a host-resident field keeps
+  // the gather stage busy long enough to matter: it reads over PCIe.
+  size_t pad = 0;
+  const int occ = R <= 4 ? 8 : 4;
+  if (headroom && occ >= 6) {
+    const int want = occ - 2;
+    const size_t per_sm = 227 * 1024, used = sizeof(VoteSmem) + 1024;
+    if (per_sm / (size_t)(want + 1) + 1024 > used) pad = per_sm / (size_t)(want + 1) + 1024 - used;
+    if (pad + used > 48 * 1024) pad = 0;       // stay within the default dynamic shared memory limit
+  }
+  if (R == 2) vote_count_kernel<2><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
+  else if (R == 4) vote_count_kernel<4><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
+  else vote_count_kernel<8><<<grid, VOTE_THREADS, pad, s>>>(p, ws, vc, item_px, chunks);
   return check_launch();
 }
   // hypotheses per thread when HN > 512 (measured at HN = 2048: 1.48 ms with 4, 1.66 ms with 8)
@@ -1571,7 +1589,8 @@ extern "C" int epb_voting_run(const epb_voting_params* pp, const epb_voting_io* 
     }
 #endif
     if (!done) {
-      if (vc.fast_ok) EPB_RETURN_IF(launch_vote_ffma(p, ws, vc, s));
+      const bool headroom = p.stage == EPB_STAGE_VOTE && is_host_pointer(io->vertex);
+      if (vc.fast_ok) EPB_RETURN_IF(launch_vote_ffma(p, ws, vc, headroom, s));
       else {   // thresholds the band test cannot serve: the reference expression for every pair
         vote_exact_kernel<<<dim3((HN + 255) / 256, p.vn, p.B), 256, 0, s>>>(p, ws);
         EPB_RETURN_IF(check_launch());

@@ -92,8 +92,13 @@ def pose_pack(rt6):
     return pose7, rt34
 
 
+# LM weights of the heatmap path.  cpnp_m's weighting is an ASSUMPTION (its binary and source are absent from the
+# reference): True / "maxval" = wxx = wyy = maxval (default), "sqrt" = sqrt(maxval), False / "unit" = cpnp.
+_WEIGHTING = {False: 0, True: 1, 0: 0, 1: 1, 2: 2, "unit": 0, "maxval": 1, "sqrt": 2}
+
+
 def pose_pipeline(preds, maxvals, bbox_xy, rate, p3d_model, K, min_k=24, sel_thresh=0.8, weighted=True):
-    """val.py:172-228 for a batch, one stream-ordered call.
+    """val.py:172-228 for a batch, one stream-ordered call.  `weighted`: True / "maxval", "sqrt", False / "unit".
     preds [B,Kp,2] f32 (crop px), maxvals [B,Kp] f32, bbox_xy [B,2], rate [B], p3d_model [Kp,3], K [3,3].
     -> dict(pose7 [B,7] f32, rt6 [B,6] f64, epnp_rt34 [B,3,4] f64, status [B] i32)."""
     dev = preds.device
@@ -108,7 +113,7 @@ def pose_pipeline(preds, maxvals, bbox_xy, rate, p3d_model, K, min_k=24, sel_thr
     with torch.cuda.device(dev):
         st = _lib.load().epb_pose_pipeline(_lib.ptr(preds), _lib.ptr(maxvals), _lib.ptr(bbox_xy), _lib.ptr(rate),
                                            _lib.ptr(p3d_model), _lib.ptr(K), b, kp, int(min_k), float(sel_thresh),
-                                           int(bool(weighted)), _lib.ptr(pose7), _lib.ptr(rt6), _lib.ptr(epnp),
+                                           _WEIGHTING[weighted], _lib.ptr(pose7), _lib.ptr(rt6), _lib.ptr(epnp),
                                            _lib.ptr(status), _lib.stream_ptr())
     _lib.check(st, "epb_pose_pipeline")
     return dict(pose7=pose7, rt6=rt6, epnp_rt34=epnp, status=status)

@@ -245,7 +245,9 @@ int epb_p3p(const double* p3d, int p3d_batched, const double* p2d, const double*
 /* val.py:172-228 batched.  preds [B,K,2] f32 crop px, maxvals [B,K] f32, bbox_xy [B,2] f64,
  * rate [B] f64, p3d_model [K,3] f64 (shared) , Kmat [9] f64.
  * Selects large_k = max(#(maxval > sel_thresh), min_k) best keypoints (ties: lower index),
- * un-crops, EPnP-RANSAC, LM with maxval weights (weighted != 0) -> pose7 [B,7] f32, rt6 [B,6]. */
+ * un-crops, EPnP-RANSAC, LM -> pose7 [B,7] f32, rt6 [B,6].  weighted: 0 unit weights (cpnp.cpnp), 1 wxx = wyy =
+ * maxval (cpnp.cpnp_m as ASSUMED in SURVEY.md 8c -- the cpnp binary and source are absent from the reference),
+ * 2 wxx = wyy = sqrt(maxval) (the other plausible reading, for users who know their cpnp build). */
 int epb_pose_pipeline(const float* preds, const float* maxvals, const double* bbox_xy,
                       const double* rate, const double* p3d_model, const double* Kmat, int B, int K,
                       int min_k, double sel_thresh, int weighted, float* pose7, double* rt6,

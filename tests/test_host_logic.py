@@ -117,3 +117,8 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "config[1]" in d["config"]["workload"]
+    # both arms print the SAME config object (the driver compares them key by key)
+    sys.path.insert(0, root)
+    import bench
+    a = bench.parse.__globals__["argparse"].Namespace(batch=64, size=256, vn=11, hn=512, fg=0.25, gpus=1)
+    assert d["config"] == bench.config_dict(a, 1)

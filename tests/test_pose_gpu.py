@@ -62,6 +62,68 @@ def test_pnp_batch_vs_cv2_with_outliers(cuda_dev):
         assert np.linalg.norm(rt[i, :, 3] - tv.ravel()) / np.linalg.norm(tv) < T_TOL_REL, i
 
 
+def test_ransac_candidates_in_parallel_equal_the_sequential_loop(cuda_dev):
+    """The kernel evaluates RANSAC iterations W at a time (W = 8, 4 or 2 warps per image, chosen by the batch size)
+    and replays OpenCV's sequential bookkeeping over the results: consensus sets and poses must equal cv2's for up
+    to 4 gross outliers in 11 points, and must not depend on W."""
+    from esa_pose_estimation_b200 import pnp as P
+    cases = [make_pose_case(7000 + i, 11, 0.6, i % 5) for i in range(40)]
+    p3 = np.stack([c["p3d"] for c in cases]); p2 = np.stack([c["p2d"] for c in cases])
+    K_d = torch.from_numpy(ESA_K).to(cuda_dev)
+
+    def run(reps):       # batch sizes 40 (W = 8), 280 (W = 4), 600 (W = 2) on a 148-SM part
+        a = torch.from_numpy(np.tile(p3, (reps, 1, 1))).to(cuda_dev)
+        b = torch.from_numpy(np.tile(p2, (reps, 1, 1))).to(cuda_dev)
+        rt, mask, status = P.pnp_batch(a, b, K_d, return_status=True)
+        return rt.cpu().numpy(), mask.cpu().numpy(), status.cpu().numpy()
+
+    rt8, m8, s8 = run(1)
+    for reps in (7, 15):
+        rt, m, st = run(reps)
+        for r in range(reps):
+            sl = slice(r * 40, (r + 1) * 40)
+            assert np.array_equal(m[sl], m8) and np.array_equal(st[sl], s8)
+            assert np.array_equal(rt[sl], rt8, equal_nan=True)          # bit-identical poses
+    n_multi = 0
+    for i, c in enumerate(cases):
+        ok, rv, tv, inl = cv2.solvePnPRansac(c["p3d"][None], c["p2d"][None], ESA_K, np.zeros((8, 1)),
+                                             reprojectionError=5.0, flags=cv2.SOLVEPNP_EPNP)
+        if not ok:
+            assert s8[i] == 1
+            continue
+        assert s8[i] == 0
+        m = 0
+        for k in inl.ravel():
+            m |= 1 << int(k)
+        assert int(m8[i]) == m, i
+        n_multi += len(c["outliers"]) > 0
+        rc, _ = cv2.Rodrigues(rv)
+        assert _ang(rt8[i, :, :3], rc) < ROT_TOL_DEG, i
+        assert np.linalg.norm(rt8[i, :, 3] - tv.ravel()) / np.linalg.norm(tv) < T_TOL_REL, i
+    assert n_multi >= 20
+
+
+def test_pose_pipeline_nan_keypoint_fails_cleanly(cuda_dev):
+    """decode_kernel returns NaN for a heatmap that contains a NaN (NaN-is-max policy): the frame must come back
+    as EPB_POSE_FAILED with a NaN pose, and its neighbours in the batch must be untouched."""
+    from esa_pose_estimation_b200 import pnp as P
+    model = tango_model(11, seed=9)
+    cases = [make_pose_case(8100 + i, 11, 0.3, 0, model=model) for i in range(3)]
+    preds = np.stack([c["p2d"] for c in cases]).astype(np.float32)
+    maxv = np.full((3, 11), 0.9, np.float32)
+    maxv[1, 4] = np.nan; preds[1, 4] = np.nan
+    zeros2 = torch.zeros((3, 2), dtype=torch.float64, device=cuda_dev)
+    ones = torch.ones((3,), dtype=torch.float64, device=cuda_dev)
+    out = P.pose_pipeline(torch.from_numpy(preds).to(cuda_dev), torch.from_numpy(maxv).to(cuda_dev), zeros2, ones,
+                          torch.from_numpy(model).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev), min_k=11)
+    st = out["status"].cpu().numpy()
+    assert st[0] == 0 and st[2] == 0 and st[1] == 1
+    assert np.isnan(out["pose7"][1].cpu().numpy()).all() and np.isfinite(out["pose7"][[0, 2]].cpu().numpy()).all()
+    ref = P.pose_pipeline(torch.from_numpy(preds[[0, 2]]).to(cuda_dev), torch.from_numpy(maxv[[0, 2]]).to(cuda_dev),
+                          zeros2[:2], ones[:2], torch.from_numpy(model).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev), min_k=11)
+    assert np.array_equal(out["rt6"][[0, 2]].cpu().numpy(), ref["rt6"].cpu().numpy())
+
+
 def test_pnp_failure_and_too_few(cuda_dev):
     from esa_pose_estimation_b200 import pnp as P
     rng = np.random.default_rng(3)
@@ -214,6 +276,35 @@ def test_lm_sweep_properties(cuda_dev):
     out2 = P.lm_refine_batch(torch.from_numpy(p2).to(cuda_dev), torch.from_numpy(model).to(cuda_dev),
                              torch.from_numpy(w).to(cuda_dev), torch.from_numpy(ESA_K).to(cuda_dev), out)
     assert (out2 - out).abs().max().item() < 1e-7
+
+
+def test_lm_sweep_at_full_size_with_an_oracle_checked_sample(cuda_dev):
+    """BASELINE config[4] at its largest size (1e6 poses x 11 points, noisy observations so that the minimiser is not
+    the planted pose): 256 poses picked across the batch equal the oracle's LM (C restatement of uncertainty_pnp.cpp)
+    within the north-star tolerances; duplicated inputs give bit-identical outputs wherever they sit in the batch."""
+    from esa_pose_estimation_b200 import pnp as P
+    rng = np.random.default_rng(21)
+    base, n, reps = 1000, 11, 1000
+    model = tango_model(n, seed=9)
+    p2 = np.zeros((base, n, 2)); init = np.zeros((base, 6))
+    for i in range(base):
+        c = make_pose_case(31000 + i, n, 0.5, 0, model=model)
+        p2[i] = c["p2d"]
+        init[i] = np.concatenate([c["rvec"] + rng.normal(0, np.deg2rad(2.0) / np.sqrt(3), 3), c["t"] * (1 + rng.normal(0, 0.02, 3))])
+    w = np.ones((base, n, 3)); w[:, :, 1] = 0
+    w[:, :, 0] = w[:, :, 2] = rng.uniform(0.3, 1.0, (base, n))            # maxval-style weights (cpnp_m)
+    P2 = torch.from_numpy(p2).to(cuda_dev).repeat(reps, 1, 1)
+    I = torch.from_numpy(init).to(cuda_dev).repeat(reps, 1)
+    Wt = torch.from_numpy(w).to(cuda_dev).repeat(reps, 1, 1)
+    out = P.lm_refine_batch(P2, torch.from_numpy(model).to(cuda_dev), Wt, torch.from_numpy(ESA_K).to(cuda_dev), I)
+    assert out.shape == (base * reps, 6) and bool(torch.isfinite(out).all())
+    o = out.view(reps, base, 6)
+    assert bool((o == o[0:1]).all())                                       # same input -> same bits, anywhere in the batch
+    o0 = o[0].cpu().numpy()
+    for i in rng.choice(base, 256, replace=False):
+        ref = opose.lm_refine(p2[i], model, w[i], ESA_K, init[i])
+        assert _ang(rodrigues(o0[i, :3]), rodrigues(ref[:3])) < ROT_TOL_DEG, i
+        assert np.linalg.norm(o0[i, 3:] - ref[3:]) / np.linalg.norm(ref[3:]) < T_TOL_REL, i
 
 
 def test_cov_to_weights_and_uncertainty_pnp_match_oracle(cuda_dev):

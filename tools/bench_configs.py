@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 from esa_pose_estimation_b200 import _lib, inference, pipeline, pnp as gp, ransac_voting_gpu as rv  # noqa: E402
 from tests.synth import ESA_K, make_pose_case, make_vertex_field, tango_model  # noqa: E402
 
-DEV = torch.device("cuda", 0)
+DEV = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
 PEAK = 6552.3
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -215,6 +215,122 @@ def c2s():
             "unit": "poses/s", "value": out[0]["poses_per_s"], "cases": out,
             "note": "with a few hundred voting pixels per image the call is a chain of short kernels (launch/latency bound): "
                     "the field bytes SURVEY 8d counts are never read, only the mask and the foreground's field"}
+
+
+# ----------------------------------------------------------------------------- pieces bench.py times itself
+def make_c3_step(n_frames, seed=2, s=384, kp=11):
+    """config[2]: `n_frames` frames of the 3000-frame validation set (this rank's share), one call."""
+    hm, bbox, rate, model = heatmap_batch(n_frames, kp, s, seed)
+    K = torch.from_numpy(ESA_K).to(DEV)
+
+    def step():
+        return pipeline.poses_from_heatmaps(hm, bbox, rate, model, K, min_k=8)["pose7"]
+    return step, {"frames": n_frames, "heatmap_bytes": hm.numel() * 4, "hm": hm}
+
+
+def make_c5_step(n_poses, seed=5):
+    """config[4]: LM refinement of `n_poses` poses (this rank's share), 11-point model, start 2 deg / 2 % off."""
+    model = tango_model(11, seed=9)
+    K = torch.from_numpy(ESA_K).to(DEV)
+    rng = np.random.default_rng(seed)
+    base = min(1000, n_poses)
+    p2d = np.zeros((base, 11, 2)); init = np.zeros((base, 6))
+    for i in range(base):
+        c = make_pose_case(9000 + i, 11, 0.5, 0, model=model)
+        p2d[i] = c["p2d"]
+        init[i, :3] = c["rvec"] + rng.normal(0, np.deg2rad(2.0) / np.sqrt(3), 3)
+        init[i, 3:] = c["t"] * (1 + rng.normal(0, 0.02, 3))
+    reps = (n_poses + base - 1) // base
+    p2 = torch.from_numpy(np.tile(p2d, (reps, 1, 1))[:n_poses]).to(DEV)
+    it = torch.from_numpy(np.tile(init, (reps, 1))[:n_poses]).to(DEV)
+    w = torch.ones((n_poses, 11, 3), dtype=torch.float64, device=DEV); w[:, :, 1] = 0
+    m = torch.from_numpy(model).to(DEV)
+
+    def step():
+        return gp.lm_refine_batch(p2, m, w, K, it)
+    return step, {"poses": n_poses, "p2d": p2d, "init": init, "model": model}
+
+
+def pose_stress():
+    """Pose solve under RANSAC pressure: 64 frames x 11 keypoints, clean / one outlier / two outliers /
+    no consensus at all (random keypoints: all 100 RANSAC iterations run and fail)."""
+    model = tango_model(11, seed=9)
+    K = torch.from_numpy(ESA_K).to(DEV)
+    m = torch.from_numpy(model).to(DEV)
+    out = {}
+    rng = np.random.default_rng(4)
+    for tag, n_out in (("clean", 0), ("one_outlier", 1), ("two_outliers", 2), ("no_consensus", -1)):
+        if n_out >= 0:
+            kp = np.stack([make_pose_case(6000 + i, 11, 0.5, n_out, model=model)["p2d"] for i in range(64)])
+        else:
+            kp = rng.uniform(0, 1900, (64, 11, 2))
+        k_t = torch.from_numpy(kp.astype(np.float32)).to(DEV)
+        ms = timed(lambda: pipeline.poses_from_keypoints(k_t, m, K)["pose7"], 20)
+        st = pipeline.poses_from_keypoints(k_t, m, K)["status"]
+        out[tag] = {"ms_per_64_frames": ms, "failed": int((st != 0).sum())}
+    return out
+
+
+def cpu_heatmap_path(n_frames, kp=11, s=128, cores=None):
+    """CPU leg of the heatmap path (configs 0 and 2): the reference's per-frame loop (val.py:151-228) through the
+    oracle port (oracle/decode.py = inference.py's get_max_preds / get_final restated and pinned bit-equal to them;
+    oracle/pose.py = pnp.py's cv2 call + the C LM), one process per core.  -> frames/s."""
+    import multiprocessing as mp
+    import time
+    cores = cores or (os.cpu_count() or 1)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_heatmap_frame, [(i, kp, s) for i in range(cores)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_heatmap_frame, [(i, kp, s) for i in range(n_frames)], chunksize=max(1, n_frames // (4 * cores)))
+        dt = time.perf_counter() - t0
+    return n_frames / dt, dt, cores
+
+
+def _cpu_heatmap_frame(args):
+    i, kp, s = args
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import decode as odec, pose as opose
+    model = tango_model(kp, seed=9)
+    c = make_pose_case(777 + i, kp, 0.0, 0, model=model)
+    lo, hi = c["p2d"].min(0), c["p2d"].max(0)
+    size = (hi - lo).max() * 1.3 + 8
+    bbox = (lo + hi) / 2 - size / 2
+    rate = s / size
+    crop = (c["p2d"] - bbox) * rate
+    ys, xs = np.mgrid[0:s, 0:s].astype(np.float32)
+    hm = np.exp(-((xs[None] - crop[:, 0, None, None]) ** 2 + (ys[None] - crop[:, 1, None, None]) ** 2) / 8.0).astype(np.float32)[None] * 0.9
+    preds, maxvals, _ = odec.decode_frame(hm)
+    return opose.frame_pose(preds, maxvals, bbox, rate, model, ESA_K, min_k=8)["t"]
+
+
+def cpu_lm_sweep(n_poses, cores=None):
+    """CPU leg of config[4]: the C restatement of uncertainty_pnp.cpp (oracle/lm_oracle.c; stand-in for cpnp, whose binary
+    and source are absent), one process per core.  -> poses/s."""
+    import multiprocessing as mp
+    import time
+    cores = cores or (os.cpu_count() or 1)
+    per = max(1, n_poses // cores)
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_lm_chunk, [(i, 50) for i in range(cores)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_lm_chunk, [(i, per) for i in range(cores)])
+        dt = time.perf_counter() - t0
+    return per * cores / dt, dt, cores
+
+
+def _cpu_lm_chunk(args):
+    seed, n = args
+    from oracle import pose as opose
+    model = tango_model(11, seed=9)
+    rng = np.random.default_rng(seed)
+    cases = [make_pose_case(9000 + (seed * 131 + i) % 1000, 11, 0.5, 0, model=model) for i in range(min(n, 64))]
+    w = np.ones((11, 3)); w[:, 1] = 0
+    inits = [np.concatenate([c["rvec"] + rng.normal(0, np.deg2rad(2.0) / np.sqrt(3), 3), c["t"] * (1 + rng.normal(0, 0.02, 3))]) for c in cases]
+    for i in range(n):
+        c = cases[i % len(cases)]
+        opose.lm_refine(c["p2d"], model, w, ESA_K, inits[i % len(cases)])
+    return n
 
 
 if __name__ == "__main__":

@@ -19,5 +19,5 @@ _lib.LIB_PATH = build.build_tuning()
 import bench  # noqa: E402
 
 if __name__ == "__main__":
-    sys.argv += ["--no-e2e", "--no-cpu-baseline"]
+    sys.argv += ["--no-cpu-baseline", "--no-configs"] + ([] if os.environ.get("EPB_AB_E2E") else ["--no-e2e"])
     bench.run_ours(bench.parse())

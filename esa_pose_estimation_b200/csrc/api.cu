@@ -1,6 +1,7 @@
 // Library-level entry points of the C ABI (include/esa_pose_b200.h).
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -8,21 +9,21 @@ namespace epb {
 thread_local int g_last_cuda_error = 0;
 unsigned long long g_launch_count = 0;
 
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};   // read on every launch without the mutex
 static std::mutex g_prof_mu;
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 static thread_local cudaEvent_t g_prof_open[PROF_CLASSES];
 
 void prof_begin(int cls, cudaStream_t s) {
-  if (!g_prof_on) return;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
   cudaEvent_t a;
   if (cudaEventCreate(&a) != cudaSuccess) return;
   cudaEventRecord(a, s);
   g_prof_open[cls] = a;
 }
 void prof_end(int cls, cudaStream_t s) {
-  if (!g_prof_on || !g_prof_open[cls]) return;
+  if (!g_prof_on.load(std::memory_order_relaxed) || !g_prof_open[cls]) return;
   cudaEvent_t b;
   if (cudaEventCreate(&b) != cudaSuccess) return;
   cudaEventRecord(b, s);
@@ -34,7 +35,7 @@ void prof_end(int cls, cudaStream_t s) {
 
 extern "C" int epb_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(epb::g_prof_mu);
-  epb::g_prof_on = on != 0;
+  epb::g_prof_on.store(on != 0, std::memory_order_relaxed);
   if (!on) {
     for (auto& r : epb::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     epb::g_prof.clear();

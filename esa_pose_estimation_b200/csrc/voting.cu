@@ -17,10 +17,10 @@
 //
 // Bit-exactness: every float operation of the reference kernels is issued through explicit
 // round-to-nearest intrinsics in the order the reference SASS executes them, so
-// nvcc cannot re-contract them.  vote_count decides each (hypothesis, pixel) pair with a
-// division/sqrt-free squared-cosine test whose error bound is proven in DESIGN.md; only pairs
-// within 2^-20 of the threshold fall through to the exact IEEE path, so the counts equal the
-// reference's integers.
+// nvcc cannot re-contract them.  vote_count decides each (hypothesis, pixel) pair with two affine
+// forms of the hypothesis (no division, no square root) and a band whose width is derived in
+// DESIGN.md section 5; only the pairs inside the band (~4e-4 of them at T = 0.999) are re-evaluated
+// with the reference expression itself, so the counts equal the reference's integers.
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
@@ -556,7 +556,8 @@ hypothesis_kernel(epb_voting_params p, Workspace ws, HypCtx hc,
 //             the reference's c is within 9.04 ulp-units of the exact cosine; gamma and EH cover that
 //             plus every rounding of the forms above, and the |d| < 1e-6 guard)
 //   else    : the warp evaluates the reference expression itself (IEEE sqrt / div), rare.
-// 8 FP32 lane-ops (FMA pipe) + 1 FSETP per test instead of ~35; counts are exact integers.
+// 6 FP32 lane-operations (5 of them as packed FFMA2 over two hypotheses) + 1 FSETP + 1 LEA.HI per test:
+// ~7.1 issue slots instead of ~35; counts are exact integers.
 // ------------------------------------------------------------------------------------------
 // Blackwell packed FP32 (FADD2 / FMUL2 / FFMA2): two hypotheses per issue slot, each half with the
 // same IEEE round-to-nearest result as the scalar instruction.
@@ -1659,7 +1660,18 @@ extern "C" int epb_voting_for_hypothesis_vanishing_point(const float* direct, co
                                                          int vn, int hn, float thresh, void* stream) {
   EPB_INIT_ONCE_PER_DEVICE(voting_kernel_attributes);
   if (!direct || !coords || !hypo3 || !inliers || tn <= 0 || vn <= 0 || hn <= 0) return EPB_ERR_INVALID;
-  if ((long long)hn * vn > 65535) return EPB_ERR_INVALID;
+  if ((long long)hn * vn > 65535) {
+    // grid.y limit: process in slabs of hypotheses (like epb_voting_for_hypothesis)
+    const int per = 65535 / vn;
+    if (per < 1) return EPB_ERR_INVALID;
+    for (int h0 = 0; h0 < hn; h0 += per) {
+      const int n = hn - h0 < per ? hn - h0 : per;
+      voting_for_hypothesis_vp_kernel<<<dim3((tn + 255) / 256, n * vn), 256, 0, (cudaStream_t)stream>>>(
+          direct, coords, hypo3 + (size_t)h0 * vn * 3, inliers + (size_t)h0 * vn * tn, tn, vn, n, thresh);
+      EPB_RETURN_IF(check_launch());
+    }
+    return EPB_OK;
+  }
   voting_for_hypothesis_vp_kernel<<<dim3((tn + 255) / 256, hn * vn), 256, 0, (cudaStream_t)stream>>>(
       direct, coords, hypo3, inliers, tn, vn, hn, thresh);
   return check_launch();

@@ -380,6 +380,31 @@ def test_vanishing_point_primitives_bit_exact_vs_reference_kernels(cuda_dev, kin
         np.testing.assert_array_equal(inl_c, inl_ref.cpu().numpy())
 
 
+def test_vote_primitives_slab_past_the_grid_limit(cuda_dev):
+    """hn * vn > 65535 (the grid.y limit): both pybind-level vote entries process the hypotheses in slabs and must
+    equal the C restatement (the vanishing-point twin used to reject such calls)."""
+    from esa_pose_estimation_b200 import ransac_voting
+    coords, direct = _compact_case(9, 24, 24, 3, 0.5, "structured")
+    tn, vn, _ = direct.shape
+    hn = 65535 // vn + 37
+    rng = np.random.default_rng(9)
+    idxs = rng.integers(0, tn, (hn, vn, 2)).astype(np.int32)
+    d_t, c_t, i_t = (torch.from_numpy(a).to(cuda_dev) for a in (direct, coords, idxs))
+    hyp = ransac_voting.generate_hypothesis(d_t, c_t, i_t)
+    inl = torch.zeros((hn, vn, tn), dtype=torch.uint8, device=cuda_dev)
+    ransac_voting.voting_for_hypothesis(d_t, c_t, hyp, inl, 0.99)
+    inl_c = np.zeros((hn, vn, tn), np.uint8)
+    ov.voting_for_hypothesis(direct, coords, hyp.cpu().numpy(), inl_c, 0.99)
+    np.testing.assert_array_equal(inl.cpu().numpy(), inl_c)
+    hyp3 = ransac_voting.generate_hypothesis_vanishing_point(d_t, c_t, i_t)
+    inl = torch.zeros((hn, vn, tn), dtype=torch.uint8, device=cuda_dev)
+    ransac_voting.voting_for_hypothesis_vanishing_point(d_t, c_t, hyp3, inl, 0.99)
+    inl_c = np.zeros((hn, vn, tn), np.uint8)
+    ov.voting_for_hypothesis_vanishing_point(direct, coords, hyp3.cpu().numpy(), inl_c, 0.99)
+    np.testing.assert_array_equal(inl.cpu().numpy(), inl_c)
+    assert inl_c[-30:].any()                                            # the last slab did real work
+
+
 @pytest.mark.parametrize("hn,rounds", [(1024, 1), (384, 3), (130, 1)])
 def test_counts_bit_exact_for_large_hypothesis_sets(cuda_dev, hn, rounds):
     """More than 512 hypotheses per keypoint switch vote_count to 8 hypotheses per thread and several

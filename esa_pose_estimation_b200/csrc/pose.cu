@@ -519,6 +519,10 @@ __device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, i
   compute_r_and_t3(ws, be, al, pw, u, v, active, n, first_lane, pw0, cam, lane, best);
 }
 
+#ifdef EPB_TUNING
+__constant__ int c_ransac_round0_warps = 4;   // EPB_RANSAC_R0: warps of round 0 (measurements only)
+#endif
+
 // cv::RNG (multiply-with-carry), seed (uint64)-1 as RANSACPointSetRegistrator::run uses
 struct CvRng {
   unsigned long long state;
@@ -590,7 +594,11 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   for (int round = 0; it0 < niters; ++round) {
     // Round 0 is what a clean frame pays: at most four warps work in it (one per scheduler: the critical warps 0
     // and 1 do not share issue slots), warp 1 on the speculative solve; warps 4.. join from round 1 on.
+#ifdef EPB_TUNING
+    const int W0 = min(W, max(2, c_ransac_round0_warps));
+#else
     constexpr int W0 = W < 4 ? W : 4;
+#endif
     const int slots = round == 0 ? W0 - 1 : W;
     const int my_slot = round == 0 ? (warp == 0 ? 0 : warp - 1) : warp;
     const bool speculative = round == 0 && warp == 1;
@@ -1328,6 +1336,9 @@ static inline int ransac_warps(int B) {
 }
 
 static void pose_kernel_attributes() {
+#ifdef EPB_TUNING
+  { const int r0 = tuning_int("EPB_RANSAC_R0", 4); cudaMemcpyToSymbol(c_ransac_round0_warps, &r0, sizeof(int)); }
+#endif
   prefer_max_shared(pnp_kernel<2>); prefer_max_shared(pnp_kernel<4>); prefer_max_shared(pnp_kernel<8>);
   prefer_max_shared(lm_kernel); prefer_max_shared(pose_pack_kernel);
   prefer_max_shared(rt34_to_rt6_kernel); prefer_max_shared(cov_to_weights_kernel);

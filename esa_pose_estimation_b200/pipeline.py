@@ -204,7 +204,7 @@ def _poses_from_host_vertex(mask, vertex, p3d_model, K, hn, thresh, min_num, max
     gs, vs = pipe.gs, pipe.vs
     bounds = [shard_range(b, i, chunks) for i in range(chunks)]
     per = max(e - s for s, e in bounds)
-    need = _voting.workspace_bytes(per, h, w, vn, hn)
+    need = _voting.workspace_bytes(per, h, w, vn, hn, max_num=max_num, philox=kw.get("idxs") is None)
     turn = pipe.turn
     # At most DEPTH calls in flight: the host waits (spinning on an event) for the call that used this
     # workspace set DEPTH turns ago.  Without it a host that enqueues faster than the GPU drains fills the

@@ -209,11 +209,13 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
     return out
 
 
-def workspace_bytes(b, h, w, vn, hn, rounds=1):
-    """Bytes of caller-owned workspace one run over [b,h,w,vn,2] needs (+ alignment slack)."""
+def workspace_bytes(b, h, w, vn, hn, rounds=1, max_num=30000, philox=True):
+    """Bytes of caller-owned workspace one run over [b,h,w,vn,2] needs (+ alignment slack).  With the torch-compatible
+    Philox draws (the default) the size is bounded by max_num, with explicit idxs / selection by h * w."""
     p = _lib.VotingParams()
     p.mode, p.B, p.H, p.W, p.vn, p.hn, p.rounds = _lib.VOTE_V3, b, h, w, vn, int(hn), int(rounds)
-    p.rng_mode = _lib.RNG_PHILOX
+    p.max_num = int(max_num)
+    p.rng_mode = _lib.RNG_PHILOX if philox else _lib.RNG_IDXS
     n = _lib.load().epb_voting_workspace_bytes(p)
     if n == 0:
         raise RuntimeError("epb_voting_workspace_bytes: invalid parameters")

@@ -163,6 +163,51 @@ def test_degenerate_and_thresholds(cuda_dev):
         np.testing.assert_array_equal(c.cpu().numpy(), c_o)
 
 
+def test_workspace_bound_drops_an_overfull_image_instead_of_overrunning(cuda_dev):
+    """The workspace holds max_num + 8 sigma + 1024 voting pixels per image when the subsample draws come from Philox
+    (DESIGN.md section 3).  Caller-supplied `selection` draws can defeat that bound (all zeros keep every pixel): the image
+    must come back flagged (NaN keypoints, status 3) and its neighbours must be untouched -- never an out-of-bounds write."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    b, s, vn, hn, max_num = 3, 96, 3, 64, 100
+    mask, vertex, _ = make_vertex_field(33, b, s, s, vn, 0.9)            # ~8300 foreground pixels > max_num: subsample applies
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev))
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    sel = torch.rand((b, s, s), device=cuda_dev)                          # ordinary draws: ~100 pixels kept per image
+    sel[1] = 0.0                                                          # image 1 keeps all ~8300 > cap (1280)
+    torch.manual_seed(5)
+    out = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn, max_num=max_num, selection=sel)
+    st, pts, tn = out["status"].cpu().numpy(), out["pts"].cpu().numpy(), out["tn"].cpu().numpy()
+    assert (st[1] == 3).all() and np.isnan(pts[1]).all() and tn[1] == 0
+    assert (st[[0, 2]] == 0).all() and np.isfinite(pts[[0, 2]]).all() and (tn[[0, 2]] > 40).all() and (tn[[0, 2]] < 200).all()
+    # the same call without the overfull image gives the same keypoints for the others (same draws, same generator offsets)
+    torch.manual_seed(5)
+    sel2 = sel.clone(); sel2[1] = 1.0                                     # image 1 keeps nothing -> fewer than min_num -> skipped
+    out2 = rv.voting_debug(_lib.VOTE_V3, m_t, vert, hn, max_num=max_num, selection=sel2)
+    np.testing.assert_array_equal(out2["pts"].cpu().numpy()[[0, 2]], pts[[0, 2]])
+
+
+def test_workspace_is_not_overrun(cuda_dev):
+    """compute-sanitizer is closed on this pool: a caller-owned workspace of exactly the advertised size, followed by a
+    guard region, must come back with the guard intact for ragged batches, the subsample and every driver mode."""
+    from esa_pose_estimation_b200 import _lib, ransac_voting_gpu as rv
+    b, s, vn, hn = 5, 72, 4, 96
+    mask, vertex, _ = make_vertex_field(41, b, s, s, vn, 0.6)
+    mask[1, 10:, :] = 0                                                  # ragged: few pixels
+    mask[3] = 1                                                          # everything foreground
+    vert = rv.vertex_layer_reshape(torch.from_numpy(vertex).to(cuda_dev))
+    m_t = torch.from_numpy(mask).to(cuda_dev)
+    guard = 1 << 16
+    for mode, kw in ((_lib.VOTE_V3, dict(max_num=30000)), (_lib.VOTE_V5, dict(max_num=100)), (_lib.VOTE_V3, dict(max_num=900)),
+                     (_lib.VOTE_DISTRIBUTION, dict(max_num=30000, rounds=3, topk=32))):
+        need = rv.workspace_bytes(b, s, s, vn, hn, rounds=kw.get("rounds", 1), max_num=kw["max_num"])
+        ws = torch.full((need + guard,), 0xA5, dtype=torch.uint8, device=cuda_dev)
+        torch.manual_seed(3)
+        out = rv._run(mode, m_t, vert, hn, kw.get("rounds", 1), 0.99, 5, kw["max_num"], topk=kw.get("topk", 0), workspace=ws)
+        torch.cuda.synchronize()
+        assert bool((ws[need:] == 0xA5).all()), (mode, kw)
+        assert all(bool(torch.isfinite(v.float()).all()) for k, v in out.items() if k in ("pts", "mean", "cov"))
+
+
 def test_distribution_matches_oracle(cuda_dev):
     from esa_pose_estimation_b200 import ransac_voting_gpu as rv
     b, h, w, vn = 2, 64, 64, 5

@@ -43,7 +43,7 @@ def main():
     pay_d = torch.empty((payload,), dtype=torch.uint8, device=dev)
     field_d = torch.empty_like(vertex_h, device=dev)
     mask_d = mask_h.to(dev)
-    ws = torch.empty((rv.workspace_bytes(a.batch, a.size, a.size, a.vn, a.hn),), dtype=torch.uint8, device=dev)
+    ws = torch.empty((rv.workspace_bytes(a.batch, a.size, a.size, a.vn, a.hn, max_num=30000),), dtype=torch.uint8, device=dev)
     vview = rv.vertex_layer_reshape(vertex_h)
 
     def barrier():

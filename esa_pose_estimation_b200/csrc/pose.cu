@@ -24,20 +24,63 @@ namespace epb {
 constexpr int POSE_WARPS = 4;
 
 struct WarpScratch {
-  double A[12][12];  // M^T M, destroyed by the eigen-solver
-  double V[12][12];  // eigenvectors (columns)
-  double S[40];      // reduced sums / scratch
+  double A[12][14];  // M^T M, destroyed by the eigen-solver (rows padded: 16-byte aligned pairs, fewer bank conflicts)
+  double V[12][14];  // eigenvectors (columns)
+  double S[80];      // reduced sums / scratch
   double L[6][10];
   double vs[4][12];  // the four null-space vectors, ascending eigenvalue
   int order[12];
+  unsigned short rr[11][6];   // round-robin schedule of the eigen-solver: p | q << 8 of pair k in round `step`
+  // the same bytes as one flat array: transposed per-point tables of the sums below (EPnP) and of LM
+  __device__ double* flat() { return reinterpret_cast<double*>(this); }
 };
-
+// Sums over the points of a frame are formed "transposed": every point lane parks its terms in a row-per-term
+// table in shared memory (row stride 33 doubles: conflict-free both ways) and lane e then adds up term e over the
+// points in index order, a short loop.  Against a butterfly per sum this is ~10x fewer instructions (a double
+// shuffle is 2 SHFL + register moves, and 40 sums x 5 stages of them were 45 KB of straight-line code that the
+// instruction cache had to stream for every solve), and the order of the additions is the sequential one of the
+// CPU implementations.
+constexpr int TSTRIDE = 33;
+constexpr int LM_ROWS = 14, LM_SUMS = 28;
+static_assert(sizeof(WarpScratch) >= (LM_ROWS * TSTRIDE + LM_SUMS) * sizeof(double), "LM scratch");
+// sum of term(p) over the points p < np, in index order like the CPU implementations (cv::mulTransposed, Eigen's
+// J^T J): 5-point EPnP samples are ill-conditioned enough for the order of these additions to decide whether a
+// borderline point is inside RANSAC's 5 px -- one of 48 consensus masks differed from OpenCV's with two
+// interleaved partial sums.  Lanes outside the point set park zeros, so no mask is needed.
+template <class F>
+__device__ __forceinline__ double sum_points(int np, F term) {
+  double s = 0.0;
+#pragma unroll 2
+  for (int p = 0; p < np; ++p) s += term(p);
+  return s;
+}
 struct Cam { double fu, fv, uc, vc; };
+
+// Phase clocks (tuning build only): thread 0 of CTA 0 accumulates the SM cycles between successive marks, read and
+// cleared through epb_debug_pose_phase_clocks (tools/pose_phases.py).  Compiles to nothing in the product library.
+#ifdef EPB_TUNING
+__device__ long long g_phase_clk[32];
+__device__ long long g_phase_last;
+#define POSE_PHASE(i)                                                   \
+  do {                                                                  \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                          \
+      const long long t_ = clock64();                                   \
+      g_phase_clk[i] += t_ - g_phase_last;                              \
+      g_phase_last = t_;                                                \
+    }                                                                   \
+  } while (0)
+#define POSE_PHASE_START()                                              \
+  do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_last = clock64(); } while (0)
+#else
+#define POSE_PHASE(i) do {} while (0)
+#define POSE_PHASE_START() do {} while (0)
+#endif
+
 
 // ------------------------------------------------------------------------------ small linear algebra
 // OpenCV cv::SVD (JacobiSVDImpl_) on a 3x3: rows of `at` are the columns of A.  Sign convention
 // matters for the EPnP control points (oracle/epnp_port.py svd_onesided_cv).
-__device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[9]) {
+__device__ __noinline__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[9]) {
   double at[3][3], v[3][3], ww[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -45,7 +88,7 @@ __device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[
     for (int j = 0; j < 3; ++j) { at[i][j] = a[j * 3 + i]; v[i][j] = (i == j) ? 1.0 : 0.0; }
 #pragma unroll
   for (int i = 0; i < 3; ++i) ww[i] = at[i][0] * at[i][0] + at[i][1] * at[i][1] + at[i][2] * at[i][2];
-  const double eps = DBL_EPSILON * 10;
+  const double eps2 = (DBL_EPSILON * 10) * (DBL_EPSILON * 10);
   for (int it = 0; it < 30; ++it) {
     bool changed = false;
 #pragma unroll
@@ -54,18 +97,20 @@ __device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[
       for (int j = i + 1; j < 3; ++j) {
         const double aa = ww[i], bb = ww[j];
         double p = at[i][0] * at[j][0] + at[i][1] * at[j][1] + at[i][2] * at[j][2];
-        if (!(fabs(p) <= eps * sqrt(aa * bb))) {
+        // OpenCV's test |p| <= eps sqrt(aa bb), squared (no square root on the serial path)
+        if (!(p * p <= eps2 * (aa * bb))) {
+          // OpenCV: p *= 2, beta = aa - bb, gamma = hypot(p, beta) and, for beta >= 0,
+          //   c = sqrt((gamma + beta) / (2 gamma)), s = p / (2 gamma c)       (beta < 0: the roles of c and s swap)
+          // computed here from two reciprocal square roots (1 / gamma and 1 / big) instead of a hypot, a square
+          // root and two divisions: the same numbers within rounding at ~200 instead of ~500 cycles per rotation.
           p *= 2.0;
-          const double beta = aa - bb, gamma = hypot(p, beta);
-          double c, s;
-          if (beta < 0) {
-            const double delta = (gamma - beta) * 0.5;
-            s = sqrt(delta / gamma);
-            c = p / (gamma * s * 2.0);
-          } else {
-            c = sqrt((gamma + beta) / (gamma * 2.0));
-            s = p / (gamma * c * 2.0);
-          }
+          const double beta = aa - bb;
+          const double g2 = fma(p, p, beta * beta);
+          const double rg = rsqrt(g2);
+          const double big2 = fma(0.5 * fabs(beta), rg, 0.5);
+          const double rb = rsqrt(big2);
+          const double big = big2 * rb, small = (0.5 * p * rg) * rb;
+          const double c = beta < 0 ? small : big, s = beta < 0 ? big : small;
           double na = 0, nb = 0;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
@@ -80,10 +125,16 @@ __device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[
       }
     if (!changed) break;
   }
+  double winv[3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) ww[i] = sqrt(at[i][0] * at[i][0] + at[i][1] * at[i][1] + at[i][2] * at[i][2]);
+  for (int i = 0; i < 3; ++i) {
+    const double ss = at[i][0] * at[i][0] + at[i][1] * at[i][1] + at[i][2] * at[i][2];
+    const double r = ss > 0 ? rsqrt(ss) : 0.0;      // 1 / w
+    winv[i] = r; ww[i] = ss * r;
+  }
   auto swap_rows = [&](int i, int j) {
     double t = ww[i]; ww[i] = ww[j]; ww[j] = t;
+    t = winv[i]; winv[i] = winv[j]; winv[j] = t;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       t = at[i][k]; at[i][k] = at[j][k]; at[j][k] = t;
@@ -101,126 +152,147 @@ __device__ void svd3_cv(const double a[9], double w[3], double ut[9], double vt[
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     w[i] = ww[i];
-    const double inv = ww[i] > 0 ? 1.0 / ww[i] : 0.0;
+    const double inv = winv[i];
 #pragma unroll
     for (int k = 0; k < 3; ++k) { ut[i * 3 + k] = at[i][k] * inv; vt[i * 3 + k] = v[i][k]; }
   }
 }
 
-// Parallel-order (round robin) Jacobi eigen-decomposition of the symmetric 12x12, REGISTER resident:
-// lane l < 12 holds the column at position l of A, lane 12 + l the column at position l of V (the
-// eigenvectors).  Every step rotates the six pairs of neighbouring positions (2k, 2k+1) at once,
-// A <- J^T A J, V <- V J, and then moves rows and columns by the fixed "tournament" permutation (position
-// 0 stays, the others go round), so that after 11 steps every pair of columns has met once and the code
-// of a step never changes: partner = lane ^ 1, all register indices static, one short loop body.  The
-// column half of the update is one exchange of the two columns of a pair (warp shuffle), the row half is
-// local to every column once the six (c, s) have been broadcast.  No shared-memory round trips and no
-// barriers inside a sweep.  Eigenvalue at position x <-> eigenvector in the V column at position x.
+// Round-robin pair (p, q) number k of round `step` for 12 indices (circle method: 11 stays, the others go round):
+// over the 11 rounds every pair of indices meets exactly once and the six pairs of a round are disjoint.
+__device__ __forceinline__ void rr_pair(int step, int k, int& p, int& q) {
+  int a = step + k; a -= a >= 11 ? 11 : 0;
+  int b = step - k; b += b < 0 ? 11 : 0;
+  p = a; q = k == 0 ? 11 : b;
+}
+
+// Parallel-order Jacobi eigen-decomposition of the symmetric 12x12 in ws.A (destroyed; eigenvalues end up on its
+// diagonal), eigenvectors in the columns of ws.V, the four of the smallest eigenvalues in ws.vs.  Both matrices
+// stay in shared memory and the warp works BY 2x2 BLOCK, not by column: a round rotates six disjoint index pairs at
+// once, A <- J^T A J, V <- V J with J = diag of six plane rotations, and under that the 2x2 block (pair I rows,
+// pair J columns) of A only mixes with itself:  B' = J_I^T B J_J.
+//   1. lanes 0..5 compute the (c, s) of their pair from three elements of A and publish them;
+//   2. lanes 0..20 own the 21 blocks I <= J: load four elements, two small products, store them and their mirror
+//      image; then all lanes rotate the 72 (row, pair) element pairs of V, at most three each.
+// Two warp barriers and ~180 warp instructions per round, against ~500 for the register-resident version of
+// round 1 (one column per lane, rows exchanged by shuffle: 39 double shuffles, two 12-way select chains to find
+// the pivot elements and a physical tournament permutation per round) -- and this is the longest serial piece of
+// a pose: 115 k of the 238 k cycles of a clean single frame before, measured with the phase clocks.
 __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
-  const bool isA = lane < 12, isV = lane >= 12 && lane < 24;
-  const int pos = isA ? lane : (isV ? lane - 12 : 0);
-  // tournament permutation pi = {0,2,4,1,6,3,8,5,10,7,11,9}: what is at position x moves to pi[x];
-  // kInv[y] = the position whose content arrives at y
-  const int inv_pos = (int)((0xa8b694725130ull >> (4 * pos)) & 15ull);
-  const int from_lane = (isV ? 12 : 0) + inv_pos;
-  double a[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) a[i] = isA ? ws.A[i][pos] : ((isV && i == pos) ? 1.0 : 0.0);
-  double off_prev = INFINITY;
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double dg = 0, off = 0;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) { if (i == pos) dg = a[i]; else off += a[i] * a[i]; }
-    off = 0.5 * warp_sum(isA ? off : 0.0);
-    double dmin = isA ? fabs(dg) : INFINITY;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, m));
-    const double tr = warp_sum(isA ? fabs(dg) : 0.0);
-    // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the
-    // null-space vectors are what EPnP needs); exact null spaces fall through to the absolute test
-    if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
-    // rounding floor: once the off-diagonal norm is at rounding level of the matrix scale AND a sweep no
-    // longer halves it, there is nothing left to remove (rank-deficient M^T M of the 5-point samples)
-    if (off < 1e-28 * tr * tr && off > 0.5 * off_prev) break;
-    off_prev = off;
-#pragma unroll 1
-    for (int step = 0; step < 11; ++step) {
-      const bool amP = (pos & 1) == 0;
-      // this column's diagonal element and its element in the partner's row
-      double dme = 0, apq = 0;
-#pragma unroll
-      for (int i = 0; i < 12; ++i) { if (i == pos) dme = a[i]; if (i == (pos ^ 1)) apq = a[i]; }
-      const double doth = __shfl_xor_sync(FULL, dme, 1);              // the partner's diagonal element
-      double c = 1.0, s = 0.0;
-      if (isA && amP && apq != 0.0) {
-        // Rotation that annihilates a_pq: the small root of  b t^2 + 2 a t - b = 0  with a = (aqq - app)/2,
-        // b = a_pq (t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) in the textbook form).  The root and
-        // c = (1 + t^2)^(-1/2) are seeded in float32 with the fast reciprocal / square roots and polished by
-        // one Newton step each in float64 (relative error ~1e-14), then renormalised to c^2 + s^2 = 1 within
-        // rounding; A is transformed with those very (c, s) (an exact orthogonal similarity, no
-        // "a_pq := 0" shortcut), so any residual a_pq is removed by the next sweep.
-        const double alpha = 0.5 * (doth - dme);
-        const double scale = fmax(fabs(alpha), fabs(apq));
-        const int e = ((__double2hiint(scale) >> 20) & 0x7ff) - 1023;   // exact power-of-two rescale, no division
-        const double inv = __hiloint2double((1023 - max(min(e, 1022), -1022)) << 20, 0);
-        const double aa = alpha * inv, bb = apq * inv;
-        const float af = fabsf((float)aa), bf = fabsf((float)bb);
-        const float tf = __fdividef(bf, af + __fsqrt_rn(af * af + bf * bf));
-        const float cf = rsqrtf(__fmaf_rn(tf, tf, 1.0f));
-        const bool plus = alpha == 0.0 || ((alpha > 0) == (apq > 0));   // sign of theta (theta = +-0 counts as +)
-        const double t0 = plus ? (double)tf : -(double)tf;
-        const double res = fma(bb * t0, t0, fma(2.0 * aa, t0, -bb));    // f(t0)
-        const double der = 2.0 * fma(bb, t0, aa);                        // f'(t0) = +-2 hypot(a, b) near the root
-        const double t1 = der != 0.0 ? t0 - res * (double)__frcp_rn((float)der) : t0;
-        const double u = fma(t1, t1, 1.0);
-        const double c0 = (double)cf;
-        const double c1 = c0 * fma(-0.5 * u, c0 * c0, 1.5);             // Newton step of y = u^(-1/2)
-        const double fix = fma(-0.5, fma(c1 * c1, u, -1.0), 1.0);       // renormalise: c^2 + s^2 = c1^2 u
-        c = c1 * fix;
-        s = t1 * c;
-      }
-      // every lane takes the (c, s) of its pair from the A lane of the pair's first column
-      c = __shfl_sync(FULL, c, pos & ~1);
-      s = __shfl_sync(FULL, s, pos & ~1);
-      // column half: [col_p, col_q] <- [c col_p - s col_q, s col_p + c col_q]   (A and V alike)
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const double o = __shfl_xor_sync(FULL, a[i], 1);
-        a[i] = amP ? fma(c, a[i], -s * o) : fma(s, o, c * a[i]);
-      }
-      // row half (A only): rows 2k, 2k+1 of every column <- J^T rows, with the (c, s) of pair k
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double ck = __shfl_sync(FULL, c, 2 * k), sk = __shfl_sync(FULL, s, 2 * k);
-        if (isA) {
-          const double rp = a[2 * k], rq = a[2 * k + 1];
-          a[2 * k] = fma(ck, rp, -sk * rq);
-          a[2 * k + 1] = fma(sk, rp, ck * rq);
-        }
-      }
-      // tournament move: rows of A (register renaming) and columns of A and V (lane exchange)
-      {
-        double bnew[12];
-        bnew[0] = a[0]; bnew[2] = a[1]; bnew[4] = a[2]; bnew[1] = a[3]; bnew[6] = a[4]; bnew[3] = a[5];
-        bnew[8] = a[6]; bnew[5] = a[7]; bnew[10] = a[8]; bnew[7] = a[9]; bnew[11] = a[10]; bnew[9] = a[11];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) a[i] = __shfl_sync(FULL, isA ? bnew[i] : a[i], from_lane);
-      }
-    }
-  }
-  // eigenvalues to the diagonal of ws.A, eigenvectors to the columns of ws.V (11 moves per sweep bring
-  // every column back to a permuted but consistent position: value at position x <-> V column x)
+  for (int e = lane; e < 144; e += 32) ws.V[e / 12][e % 12] = (e / 12 == e % 12) ? 1.0 : 0.0;
+  int bI = 0, bJ = 0;                       // this lane's block of A (lanes 0..20)
   {
-    double dg = 0;
+    int rem = lane;
+    while (bI < 5 && rem >= 6 - bI) { rem -= 6 - bI; ++bI; }
+    bJ = min(bI + rem, 5);
+  }
+  // this lane's (row, pair) items of V: item = lane + 32 m < 72, row = item / 6, pair = item % 6
+  int vr[3], vJ[3];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) if (i == pos) dg = a[i];
-    if (isA) ws.A[pos][pos] = dg;
-    if (isV) {
-#pragma unroll
-      for (int i = 0; i < 12; ++i) ws.V[i][pos] = a[i];
-    }
+  for (int m = 0; m < 3; ++m) { const int item = min(lane + 32 * m, 71); vr[m] = item / 6; vJ[m] = item - 6 * vr[m]; }
+  const bool v2 = lane + 64 < 72;
+  double* cs = ws.S;                        // [6][2]: (c, s) of the six pairs of the round
+  for (int e = lane; e < 66; e += 32) {     // the schedule as a table: one 16-bit load per pair and round
+    int p, q;
+    rr_pair(e / 6, e % 6, p, q);
+    ws.rr[e / 6][e % 6] = (unsigned short)(p | (q << 8));
   }
   __syncwarp();
+  double off_prev = INFINITY;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    // Convergence is quadratic and never there before the fourth sweep on a full matrix; the first three tests
+    // are skipped unless the matrix arrives (nearly) diagonal, which the cheap test of sweep 0 covers.
+    if (sweep == 0 || sweep >= 4) {
+      double off = 0.0, tr = 0.0, dmin = INFINITY;
+      for (int e = lane; e < 144; e += 32) {
+        const int r = e / 12, c = e - 12 * r;
+        const double v = ws.A[r][c];
+        if (r == c) { tr += fabs(v); dmin = fmin(dmin, fabs(v)); } else off += v * v;
+      }
+      off = 0.5 * warp_sum(off);
+      tr = warp_sum(tr);
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, m));
+      // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the null-space vectors
+      // are what EPnP needs); exact null spaces fall through to the absolute test
+      if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
+      // rounding floor of an exact similarity: (12 eps tr)^2 ~ 2e-30 tr^2.  The sweeps converge quadratically
+      // (off / tr^2: ... 1e-10, 1e-19, 1e-33 on this problem family), so the first sweep that lands below 1e-28 is
+      // the last useful one -- the register version ran one more to SEE the stagnation.  That test stays as the
+      // fallback.
+      if (off < 1e-28 * tr * tr) break;
+      if (off < 1e-24 * tr * tr && off > 0.5 * off_prev) break;
+      off_prev = off;
+    }
+    POSE_PHASE(20);
+#ifdef EPB_TUNING
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[23] += 1;
+#endif
+#pragma unroll 1
+    for (int step = 0; step < 11; ++step) {
+      const unsigned short* rr = ws.rr[step];
+      if (lane < 6) {
+        const int pq = rr[lane], p = pq & 0xff, q = pq >> 8;
+        const double app = ws.A[p][p], aqq = ws.A[q][q], apq = ws.A[p][q];
+        // Rotation that annihilates a_pq: t = tan(theta) is the small root of  b t^2 + 2 a t - b = 0  with
+        // a = (aqq - app)/2, b = a_pq, i.e. t = sgn(a) b / (|a| + h), h = hypot(a, b), and from it
+        //   c^2 = (h + |a|) / (2 h),   s = sgn(a) b / (2 h c).
+        // Two reciprocal square roots (1/h and 1/c) and a handful of multiplications: ~200 cycles of dependent
+        // latency, against ~800 for the float32-seeded Newton form of round 1 (MUFU and F2F conversions cost 20-45
+        // cycles each on this part, tools/micro/fp64_latency.cu).  c^2 + s^2 = 1 within rounding and A is
+        // transformed with those very (c, s) (an exact orthogonal similarity, no "a_pq := 0" shortcut), so any
+        // residual a_pq is removed by the next sweep.
+        const double alpha = 0.5 * (aqq - app);
+        const double h2 = fma(alpha, alpha, apq * apq);
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0 && h2 > 1e-290 && h2 < 1e290) {
+          const double rh = rsqrt(h2);                               // 1 / h
+          const double c2 = fma(0.5 * fabs(alpha), rh, 0.5);        // in [0.5, 1]
+          const double rc = rsqrt(c2);                               // 1 / c
+          const double hb = 0.5 * apq * rh;
+          c = c2 * rc;
+          s = alpha < 0.0 ? -(hb * rc) : hb * rc;
+        }
+        cs[2 * lane] = c; cs[2 * lane + 1] = s;
+      }
+      __syncwarp();
+      POSE_PHASE(21);
+      {
+        // all loads first, then the arithmetic, then the stores: the compiler cannot know that the items of a lane
+        // never alias and would otherwise run them one after the other, each waiting on its own loads
+        const int pqI = rr[bI], pqJ = rr[bJ];
+        const int pI = pqI & 0xff, qI = pqI >> 8, pJ = pqJ & 0xff, qJ = pqJ >> 8;
+        int pv[3], qv[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { const int pq = rr[vJ[m]]; pv[m] = pq & 0xff; qv[m] = pq >> 8; }
+        const double cI = cs[2 * bI], sI = cs[2 * bI + 1], cJ = cs[2 * bJ], sJ = cs[2 * bJ + 1];
+        const double b00 = ws.A[pI][pJ], b01 = ws.A[pI][qJ], b10 = ws.A[qI][pJ], b11 = ws.A[qI][qJ];
+        double cv[3], sv[3], vp[3], vq[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          cv[m] = cs[2 * vJ[m]]; sv[m] = cs[2 * vJ[m] + 1];
+          vp[m] = ws.V[vr[m]][pv[m]]; vq[m] = ws.V[vr[m]][qv[m]];
+        }
+        // columns: [col_p, col_q] <- [c col_p - s col_q, s col_p + c col_q]; rows likewise with the row pair's (c, s)
+        const double t00 = fma(cJ, b00, -sJ * b01), t01 = fma(sJ, b00, cJ * b01);
+        const double t10 = fma(cJ, b10, -sJ * b11), t11 = fma(sJ, b10, cJ * b11);
+        const double n00 = fma(cI, t00, -sI * t10), n10 = fma(sI, t00, cI * t10);
+        const double n01 = fma(cI, t01, -sI * t11), n11 = fma(sI, t01, cI * t11);
+        double np[3], nq[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) { np[m] = fma(cv[m], vp[m], -sv[m] * vq[m]); nq[m] = fma(sv[m], vp[m], cv[m] * vq[m]); }
+        if (lane < 21) {
+          ws.A[pI][pJ] = n00; ws.A[pI][qJ] = n01; ws.A[qI][pJ] = n10; ws.A[qI][qJ] = n11;
+          if (bI != bJ) { ws.A[pJ][pI] = n00; ws.A[qJ][pI] = n01; ws.A[pJ][qI] = n10; ws.A[qJ][qI] = n11; }
+        }
+        ws.V[vr[0]][pv[0]] = np[0]; ws.V[vr[0]][qv[0]] = nq[0];
+        ws.V[vr[1]][pv[1]] = np[1]; ws.V[vr[1]][qv[1]] = nq[1];
+        if (v2) { ws.V[vr[2]][pv[2]] = np[2]; ws.V[vr[2]][qv[2]] = nq[2]; }
+      }
+      __syncwarp();
+      POSE_PHASE(22);
+    }
+  }
   // ascending order of the eigenvalues (stable)
   if (lane == 0) {
     for (int i = 0; i < 12; ++i) ws.order[i] = i;
@@ -237,67 +309,86 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
   __syncwarp();
 }
 
-// Householder least squares, 6 x N (N <= 5), fully unrolled so everything stays in registers.
-template <int N>
-__device__ void lstsq6(double (&a)[6][N], double (&b)[6], double (&x)[N]) {
+// Householder least squares, 6 x ncols (ncols <= 5; the columns beyond ncols must be zero and get x = 0).  One
+// copy with the width as a run-time (per-lane) value serves the three beta initialisations (4, 3 and 5 columns,
+// side by side in one pass instead of three divergent ones) and the Gauss-Newton steps (epnp_core calls it from a
+// single site): the unrolled body is ~1 k instructions and used to exist four times.
+// Same reflections as OpenCV's (v = a_k - alpha e_k, alpha = -sgn(a_kk) |a_k|), arranged for latency: this is a
+// serial chain that runs 8 times per EPnP solve, and an IEEE square root or division costs 80-100 cycles on this
+// part against 9 for an FMA (tools/micro/fp64_latency.cu).  With rs = rsqrt(|a_k|^2):  |alpha| = |a_k|^2 rs,
+// v^T v = 2 |alpha| (|alpha| + |a_kk|), so 2 / v^T v = rs / (|alpha| + |a_kk|) -- one rsqrt and one reciprocal per
+// column -- and the back-substitution divides by R_kk = alpha, i.e. multiplies by -+rs, already known.  The dot
+// products run as two interleaved partial sums.
+__device__ __forceinline__ void lstsq6(double (&a)[6][5], double (&b)[6], double (&x)[5], int ncols) {
+  double rdiag[5];
 #pragma unroll
-  for (int k = 0; k < N; ++k) {
-    double nrm = 0;
+  for (int k = 0; k < 5; ++k) {
+    rdiag[k] = 0.0;
+    if (k >= ncols) continue;
+    double n0 = 0, n1 = 0;
 #pragma unroll
-    for (int i = k; i < 6; ++i) nrm += a[i][k] * a[i][k];
-    double alpha = sqrt(nrm);
-    if (alpha != 0.0) {
-      if (a[k][k] > 0) alpha = -alpha;
-      double vk[6];
+    for (int i = k; i < 6; ++i) { if ((i - k) & 1) n1 = fma(a[i][k], a[i][k], n1); else n0 = fma(a[i][k], a[i][k], n0); }
+    const double nrm = n0 + n1;
+    if (nrm != 0.0) {
+      const double rs = rsqrt(nrm), aabs = nrm * rs;
+      const double akk = a[k][k];
+      const double vkk = akk > 0 ? akk + aabs : akk - aabs;        // a_kk - alpha
+      const double inv = rs / (aabs + fabs(akk));                   // 2 / v^T v
+      rdiag[k] = akk > 0 ? -rs : rs;                                // 1 / alpha = 1 / R_kk
 #pragma unroll
-      for (int i = 0; i < 6; ++i) vk[i] = (i >= k) ? a[i][k] : 0.0;
-      vk[k] -= alpha;
-      double vn2 = 0;
+      for (int j = k + 1; j < 6; ++j) {                             // j == 5: the right-hand side
+        double d0 = vkk * (j < 5 ? a[k][j < 5 ? j : 0] : b[k]), d1 = 0;
 #pragma unroll
-      for (int i = k; i < 6; ++i) vn2 += vk[i] * vk[i];
-      if (vn2 != 0.0) {
-        const double inv = 2.0 / vn2;
-#pragma unroll
-        for (int j = k; j < N; ++j) {
-          double d = 0;
-#pragma unroll
-          for (int i = k; i < 6; ++i) d += vk[i] * a[i][j];
-          d *= inv;
-#pragma unroll
-          for (int i = k; i < 6; ++i) a[i][j] -= d * vk[i];
+        for (int i = k + 1; i < 6; ++i) {
+          const double cij = j < 5 ? a[i][j < 5 ? j : 0] : b[i];
+          if ((i - k) & 1) d1 = fma(a[i][k], cij, d1); else d0 = fma(a[i][k], cij, d0);
         }
-        double d = 0;
+        const double d = (d0 + d1) * inv;
+        if (j < 5) {
+          a[k][j < 5 ? j : 0] -= d * vkk;
 #pragma unroll
-        for (int i = k; i < 6; ++i) d += vk[i] * b[i];
-        d *= inv;
+          for (int i = k + 1; i < 6; ++i) a[i][j < 5 ? j : 0] -= d * a[i][k];
+        } else {
+          b[k] -= d * vkk;
 #pragma unroll
-        for (int i = k; i < 6; ++i) b[i] -= d * vk[i];
+          for (int i = k + 1; i < 6; ++i) b[i] -= d * a[i][k];
+        }
       }
+    } else {
+      rdiag[k] = 1.0 / a[k][k];
     }
   }
 #pragma unroll
-  for (int i = N - 1; i >= 0; --i) {
+  for (int i = 4; i >= 0; --i) {
     double s = b[i];
 #pragma unroll
-    for (int j = i + 1; j < N; ++j) s -= a[i][j] * x[j];
-    x[i] = s / a[i][i];
+    for (int j = i + 1; j < 5; ++j) s -= a[i][j] * x[j];
+    x[i] = i < ncols ? s * rdiag[i] : 0.0;
   }
 }
 
 // ------------------------------------------------------------------------------ EPnP
 struct PoseRT { double R[9]; double t[3]; double err; };
 
-// The three candidates at once: the per-point sums of all three are reduced interleaved (one reduction
-// latency instead of three), the 3x3 SVD / rotation / translation of candidate c is computed by the lanes
-// with lane % 3 == c (three different problems side by side instead of one after the other, lane-redundant
-// scalar work), and every point lane then scores all three poses.  Same arithmetic per candidate as
-// compute_r_and_t; the pose with the smallest mean reprojection error wins, ties keep the lower index.
-__device__ void compute_r_and_t3(const WarpScratch& ws, const double be[4], const double al[4],
-                                 const double pw[3], double u, double v, bool active, int n, int first_lane,
+// The three candidates at once.  Every point lane forms its camera-frame point under each candidate's betas and
+// parks the nine coordinates next to its centred model point in the transposed table; lanes 0..8 then add up the
+// nine centroid coordinates and lanes 0..26 the 3 x 9 entries of the three cross-covariances, over the points of
+// the set in index order.  The 3x3 SVD / rotation / translation of candidate c is computed by the lanes with
+// lane % 3 == c (three different problems side by side, lane-redundant scalar work), and every point lane then
+// scores all three poses.  The pose with the smallest mean reprojection error wins, ties keep the lower index.
+// Table (ws.flat()): rows 0..8 = pc[c][k], rows 9..11 = pw - pw0, then 9 centroid sums and 27 covariance sums --
+// this overlays A, V, S and L, which are all spent by now, and stays clear of ws.vs.
+__device__ void compute_r_and_t3(WarpScratch& ws, const double be[4], const double al[4],
+                                 const double pw[3], double u, double v, unsigned amask, int n, int first_lane,
                                  const double pw0[3], const Cam& cam, int lane, PoseRT& best) {
   const int mine = lane % 3;
-  double abt[9], pc0m[3];
-#pragma unroll 1
+  const bool active = (amask >> lane) & 1u;
+  double* T = ws.flat();
+  double* P0 = T + 12 * TSTRIDE;        // [3][3] centroids
+  double* CV = P0 + 9;                  // [3][9] cross-covariances
+  static_assert(12 * TSTRIDE + 36 <= 12 * 14 * 2 + 80 + 60, "the table must end before ws.vs");
+  double pcs[3][3];
+#pragma unroll
   for (int c = 0; c < 3; ++c) {
     double bc[4];
 #pragma unroll
@@ -310,26 +401,37 @@ __device__ void compute_r_and_t3(const WarpScratch& ws, const double be[4], cons
         pc[k] += al[j] * (bc[0] * ws.vs[0][3 * j + k] + bc[1] * ws.vs[1][3 * j + k] +
                           bc[2] * ws.vs[2][3 * j + k] + bc[3] * ws.vs[3][3 * j + k]);
     const double z0 = __shfl_sync(FULL, pc[2], first_lane);
-    if (z0 < 0.0) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) pc[k] = -pc[k];
-    }
-    double pc0[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) pc0[k] = warp_sum(active ? pc[k] : 0.0) / n;
-    double sum[9];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        sum[3 * j + k] = warp_sum(active ? (pc[j] - pc0[j]) * (pw[k] - pw0[k]) : 0.0);
-    if (mine == c) {
-#pragma unroll
-      for (int i = 0; i < 9; ++i) abt[i] = sum[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) pc0m[i] = pc0[i];
-    }
+    for (int k = 0; k < 3; ++k) pcs[c][k] = z0 < 0.0 ? -pc[k] : pc[k];
   }
+  __syncwarp();                          // every lane is done reading ws.L / ws.S
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T[(3 * c + k) * TSTRIDE + lane] = pcs[c][k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) T[(9 + k) * TSTRIDE + lane] = active ? pw[k] - pw0[k] : 0.0;
+  __syncwarp();
+  const int np = 32 - __clz(amask);
+  if (lane < 9) {
+    const double* row = T + lane * TSTRIDE;
+    P0[lane] = sum_points(np, [&](int p) { return row[p]; }) / n;
+  }
+  __syncwarp();
+  if (lane < 27) {
+    const int c = lane / 9, j = (lane % 9) / 3, k = lane % 3;
+    const double* pj = T + (3 * c + j) * TSTRIDE;
+    const double* wk = T + (9 + k) * TSTRIDE;
+    const double p0 = P0[3 * c + j];
+    CV[lane] = sum_points(np, [&](int p) { return (pj[p] - p0) * wk[p]; });
+  }
+  __syncwarp();
+  POSE_PHASE(8);
+  double abt[9], pc0m[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) abt[i] = CV[9 * mine + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pc0m[i] = P0[3 * mine + i];
   double w[3], ut[9], vt[9], R[9], t[3];
   svd3_cv(abt, w, ut, vt);
 #pragma unroll
@@ -342,6 +444,7 @@ __device__ void compute_r_and_t3(const WarpScratch& ws, const double be[4], cons
   if (det < 0) { R[6] = -R[6]; R[7] = -R[7]; R[8] = -R[8]; }
 #pragma unroll
   for (int i = 0; i < 3; ++i) t[i] = pc0m[i] - (R[3 * i] * pw0[0] + R[3 * i + 1] * pw0[1] + R[3 * i + 2] * pw0[2]);
+  POSE_PHASE(9);
   best.err = INFINITY;
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
@@ -366,18 +469,36 @@ __device__ void compute_r_and_t3(const WarpScratch& ws, const double be[4], cons
 __device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int first_lane,
                           const double pw_in[3], double u, double v, const Cam& cam, PoseRT& best) {
   double pw[3] = {active ? pw_in[0] : 0.0, active ? pw_in[1] : 0.0, active ? pw_in[2] : 0.0};
+  const unsigned amask = __ballot_sync(FULL, active);
+  double* T = ws.flat();                 // transposed per-point table, rows of TSTRIDE (overlays A and V)
   // control points: centroid + PCA axes (OpenCV SVD sign convention)
-  double c0[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) c0[k] = warp_sum(pw[k]) / n;
-  double d[3];
+  for (int k = 0; k < 3; ++k) T[k * TSTRIDE + lane] = pw[k];
+  __syncwarp();
+  const int np = 32 - __clz(amask);       // lanes outside the set hold zeros in every table below
+  if (lane < 3) {
+    const double* row = T + lane * TSTRIDE;
+    ws.S[lane] = sum_points(np, [&](int p) { return row[p]; }) / n;
+  }
+  __syncwarp();
+  double c0[3], d[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) d[k] = active ? pw[k] - c0[k] : 0.0;
+  for (int k = 0; k < 3; ++k) { c0[k] = ws.S[k]; d[k] = active ? pw[k] - c0[k] : 0.0; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) T[(3 + k) * TSTRIDE + lane] = d[k];
+  __syncwarp();
+  if (lane < 6) {                        // xx xy xz yy yz zz
+    const int j = lane < 3 ? 0 : (lane < 5 ? 1 : 2), k = lane < 3 ? lane : (lane < 5 ? lane - 2 : 2);
+    const double* dj = T + (3 + j) * TSTRIDE;
+    const double* dk = T + (3 + k) * TSTRIDE;
+    ws.S[4 + lane] = sum_points(np, [&](int p) { return dj[p] * dk[p]; });
+  }
+  __syncwarp();
   double cov[9];
-  cov[0] = warp_sum(d[0] * d[0]); cov[1] = warp_sum(d[0] * d[1]); cov[2] = warp_sum(d[0] * d[2]);
-  cov[4] = warp_sum(d[1] * d[1]); cov[5] = warp_sum(d[1] * d[2]); cov[8] = warp_sum(d[2] * d[2]);
+  cov[0] = ws.S[4]; cov[1] = ws.S[5]; cov[2] = ws.S[6]; cov[4] = ws.S[7]; cov[5] = ws.S[8]; cov[8] = ws.S[9];
   cov[3] = cov[1]; cov[6] = cov[2]; cov[7] = cov[5];
   double w[3], uct[9], vt_unused[9];
+  POSE_PHASE(1);
   svd3_cv(cov, w, uct, vt_unused);
   double kk[3];
 #pragma unroll
@@ -391,26 +512,32 @@ __device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, i
   }
   al[0] = 1.0 - al[1] - al[2] - al[3];
   if (!active) { al[0] = al[1] = al[2] = al[3] = 0.0; }
-  // M^T M from four families of pair sums
-  const double du = cam.uc - u, dv = cam.vc - v, q = du * du + dv * dv;
+  POSE_PHASE(2);
+  // M^T M from four families of pair sums: sum al_j al_k {1, du, dv, du^2 + dv^2}, 10 pairs j <= k each
   {
-    int e = 0;
+    const double du = cam.uc - u, dv = cam.vc - v;
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int k = j; k < 4; ++k) {
-        const double aa = al[j] * al[k];
-        const double s0 = warp_sum(aa), s1 = warp_sum(aa * du), s2 = warp_sum(aa * dv), s3 = warp_sum(aa * q);
-        if (lane == 0) { ws.S[e] = s0; ws.S[10 + e] = s1; ws.S[20 + e] = s2; ws.S[30 + e] = s3; }
-        ++e;
-      }
+    for (int j = 0; j < 4; ++j) T[j * TSTRIDE + lane] = al[j];
+    T[4 * TSTRIDE + lane] = du; T[5 * TSTRIDE + lane] = dv; T[6 * TSTRIDE + lane] = du * du + dv * dv;
+    __syncwarp();
+    for (int e = lane; e < 40; e += 32) {
+      const int fam = e / 10;
+      int j = 0, rem = e - 10 * fam;
+      while (rem >= 4 - j) { rem -= 4 - j; ++j; }
+      const double* aj = T + j * TSTRIDE;
+      const double* ak = T + (j + rem) * TSTRIDE;
+      const double* f = T + (3 + fam) * TSTRIDE;
+      ws.S[40 + e] = fam ? sum_points(np, [&](int p) { return aj[p] * ak[p] * f[p]; })
+                         : sum_points(np, [&](int p) { return aj[p] * ak[p]; });
+    }
+    __syncwarp();
   }
-  __syncwarp();
   for (int e = lane; e < 144; e += 32) {
     const int r = e / 12, c = e % 12;
     const int j = r / 3, cr = r % 3, k = c / 3, cc = c % 3;
     const int lo = j < k ? j : k, hi = j < k ? k : j;
-    const int pidx = lo * 4 - lo * (lo - 1) / 2 + (hi - lo);  // index of pair (lo,hi), lo<=hi
+    const int pidx = 40 + lo * 4 - lo * (lo - 1) / 2 + (hi - lo);  // index of pair (lo,hi), lo<=hi
     const double s0 = ws.S[pidx], s1 = ws.S[10 + pidx], s2 = ws.S[20 + pidx], s3 = ws.S[30 + pidx];
     double val;
     if (cr == 0 && cc == 0) val = s0 * cam.fu * cam.fu;
@@ -422,7 +549,9 @@ __device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, i
     ws.A[r][c] = val;
   }
   __syncwarp();
+  POSE_PHASE(3);
   jacobi_eigh12(ws, lane);
+  POSE_PHASE(4);
   // L_6x10 and rho
   {
     const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
@@ -464,59 +593,66 @@ __device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, i
   // The three beta initialisations and their Gauss-Newton refinements are independent and lane-redundant
   // scalar work: lane l carries candidate l % 3, so the 3 x 5 Gauss-Newton solves run side by side
   // (only the three different initial solves diverge); the betas are then broadcast per candidate.
+  POSE_PHASE(5);
   double be[4] = {0, 0, 0, 0};
   {
     const int cand = lane % 3;
-    if (cand == 0) {          // [B11 B12 B13 B14]
-      double a[6][4], b[6], x[4];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][3]; a[i][3] = ws.L[i][6]; b[i] = rho[i]; }
-      lstsq6<4>(a, b, x);
-      if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = -x[1] / be[0]; be[2] = -x[2] / be[0]; be[3] = -x[3] / be[0]; }
-      else { be[0] = sqrt(x[0]); be[1] = x[1] / be[0]; be[2] = x[2] / be[0]; be[3] = x[3] / be[0]; }
-    } else if (cand == 1) {   // [B11 B12 B22]
-      double a[6][3], b[6], x[3];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) { a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][2]; b[i] = rho[i]; }
-      lstsq6<3>(a, b, x);
-      if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
-      else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
-      if (x[1] < 0) be[0] = -be[0];
-    } else {                  // [B11 B12 B22 B13 B23]
-      double a[6][5], b[6], x[5];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][2]; a[i][3] = ws.L[i][3]; a[i][4] = ws.L[i][4];
-        b[i] = rho[i];
-      }
-      lstsq6<5>(a, b, x);
-      if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
-      else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
-      if (x[1] < 0) be[0] = -be[0];
-      be[2] = x[3] / be[0];
-    }
-    // 5 Gauss-Newton steps on the control-point distance constraints
+    // One loop, six passes through ONE inlined copy of the least-squares solver (everything stays in registers;
+    // out of line its arrays lived in local memory and the loads sat on the serial path):
+    //   pass 0: the initial solve -- cand 0 -> [B11 B12 B13 B14] (columns 0 1 3 6 of L), cand 1 -> [B11 B12 B22]
+    //           (0 1 2), cand 2 -> [B11 B12 B22 B13 B23] (0 1 2 3 4), side by side with a per-lane width;
+    //   passes 1..5: the Gauss-Newton steps on the control-point distance constraints.
+    const int c2 = cand == 0 ? 3 : 2, c3 = cand == 0 ? 6 : 3;
 #pragma unroll 1
-    for (int it = 0; it < 5; ++it) {
-      double a[6][4], b[6], x[4];
+    for (int pass = 0; pass < 6; ++pass) {
+      double a[6][5], b[6], x[5];
+      int ncols = 4;
+      if (pass == 0) {
+        ncols = cand == 0 ? 4 : (cand == 1 ? 3 : 5);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double* r = ws.L[i];
-        a[i][0] = 2 * r[0] * be[0] + r[1] * be[1] + r[3] * be[2] + r[6] * be[3];
-        a[i][1] = r[1] * be[0] + 2 * r[2] * be[1] + r[4] * be[2] + r[7] * be[3];
-        a[i][2] = r[3] * be[0] + r[4] * be[1] + 2 * r[5] * be[2] + r[8] * be[3];
-        a[i][3] = r[6] * be[0] + r[7] * be[1] + r[8] * be[2] + 2 * r[9] * be[3];
-        b[i] = rho[i] - (r[0] * be[0] * be[0] + r[1] * be[0] * be[1] + r[2] * be[1] * be[1] +
-                         r[3] * be[0] * be[2] + r[4] * be[1] * be[2] + r[5] * be[2] * be[2] +
-                         r[6] * be[0] * be[3] + r[7] * be[1] * be[3] + r[8] * be[2] * be[3] +
-                         r[9] * be[3] * be[3]);
+        for (int i = 0; i < 6; ++i) {
+          a[i][0] = ws.L[i][0]; a[i][1] = ws.L[i][1]; a[i][2] = ws.L[i][c2];
+          a[i][3] = cand == 1 ? 0.0 : ws.L[i][c3];
+          a[i][4] = cand == 2 ? ws.L[i][4] : 0.0;
+          b[i] = rho[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double* r = ws.L[i];
+          a[i][0] = 2 * r[0] * be[0] + r[1] * be[1] + r[3] * be[2] + r[6] * be[3];
+          a[i][1] = r[1] * be[0] + 2 * r[2] * be[1] + r[4] * be[2] + r[7] * be[3];
+          a[i][2] = r[3] * be[0] + r[4] * be[1] + 2 * r[5] * be[2] + r[8] * be[3];
+          a[i][3] = r[6] * be[0] + r[7] * be[1] + r[8] * be[2] + 2 * r[9] * be[3];
+          a[i][4] = 0.0;
+          b[i] = rho[i] - (r[0] * be[0] * be[0] + r[1] * be[0] * be[1] + r[2] * be[1] * be[1] +
+                           r[3] * be[0] * be[2] + r[4] * be[1] * be[2] + r[5] * be[2] * be[2] +
+                           r[6] * be[0] * be[3] + r[7] * be[1] * be[3] + r[8] * be[2] * be[3] +
+                           r[9] * be[3] * be[3]);
+        }
       }
-      lstsq6<4>(a, b, x);
+      POSE_PHASE(24);
+      lstsq6(a, b, x, ncols);
+      POSE_PHASE(25);
+      if (pass == 0) {
+        if (cand == 0) {
+          if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = -x[1] / be[0]; be[2] = -x[2] / be[0]; be[3] = -x[3] / be[0]; }
+          else { be[0] = sqrt(x[0]); be[1] = x[1] / be[0]; be[2] = x[2] / be[0]; be[3] = x[3] / be[0]; }
+        } else {
+          if (x[0] < 0) { be[0] = sqrt(-x[0]); be[1] = x[2] < 0 ? sqrt(-x[2]) : 0.0; }
+          else { be[0] = sqrt(x[0]); be[1] = x[2] > 0 ? sqrt(x[2]) : 0.0; }
+          if (x[1] < 0) be[0] = -be[0];
+          if (cand == 2) be[2] = x[3] / be[0];
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) be[k] += x[k];
+        for (int k = 0; k < 4; ++k) be[k] += x[k];
+      }
     }
   }
-  compute_r_and_t3(ws, be, al, pw, u, v, active, n, first_lane, pw0, cam, lane, best);
+  POSE_PHASE(7);
+  compute_r_and_t3(ws, be, al, pw, u, v, amask, n, first_lane, pw0, cam, lane, best);
+  POSE_PHASE(10);
 }
 
 #ifdef EPB_TUNING
@@ -573,6 +709,10 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   const int model_points = 5;
   inlier_mask = 0;
   if (n < model_points) return EPB_POSE_TOO_FEW;   // (uniform over the CTA: no barrier has been executed)
+  // a non-finite correspondence (decode's NaN-is-max policy hands a NaN keypoint on) fails the frame as a whole
+  // instead of silently becoming an outlier: NaN pose, EPB_POSE_FAILED (uniform over the CTA as well)
+  if (__any_sync(FULL, lane < n && !(isfinite(pw[0]) && isfinite(pw[1]) && isfinite(pw[2]) && isfinite(u) && isfinite(v))))
+    return EPB_POSE_FAILED;
   const unsigned all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
   if (n == model_points) {       // the minimal sample is the whole set: OpenCV solves it once
     if (warp == 1) {
@@ -733,13 +873,14 @@ __device__ void rotate_point_jet(const double aa[3], const double pt[3], J3 out[
   const J3 w0 = {aa[0], 1, 0, 0}, w1 = {aa[1], 0, 1, 0}, w2 = {aa[2], 0, 0, 1};
   const J3 theta2 = w0 * w0 + w1 * w1 + w2 * w2;
   if (theta2.a > DBL_EPSILON) {
-    const double th = sqrt(theta2.a);
-    const double dth = 1.0 / (2.0 * th);
+    const double ith = rsqrt(theta2.a), th = theta2.a * ith;   // one rsqrt instead of a square root and two divisions
+    const double dth = 0.5 * ith;
     const J3 theta = {th, theta2.v0 * dth, theta2.v1 * dth, theta2.v2 * dth};
-    const double c = cos(th), s = sin(th);
+    double s, c;
+    sincos(th, &s, &c);
     const J3 ct = {c, -s * theta.v0, -s * theta.v1, -s * theta.v2};
     const J3 st = {s, c * theta.v0, c * theta.v1, c * theta.v2};
-    const double ith = 1.0 / th, dith = -ith * ith;
+    const double dith = -ith * ith;
     const J3 ti = {ith, dith * theta.v0, dith * theta.v1, dith * theta.v2};
     const J3 n0 = w0 * ti, n1 = w1 * ti, n2 = w2 * ti;
     const J3 x0 = n1 * pt[2] - n2 * pt[1], x1 = n2 * pt[0] - n0 * pt[2], x2 = n0 * pt[1] - n1 * pt[0];
@@ -783,7 +924,7 @@ __device__ void residual_lane(const double x[6], const double pt[3], double u, d
 }
 
 __device__ bool ldlt_solve6(const double (&A)[6][6], const double (&b)[6], double (&x)[6]) {
-  double L[6][6], D[6];
+  double L[6][6], D[6], rD[6];
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
@@ -792,12 +933,14 @@ __device__ bool ldlt_solve6(const double (&A)[6][6], const double (&b)[6], doubl
     for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
     D[j] = d;
     if (d == 0.0 || d != d) ok = false;
+    const double rd = 1.0 / d;          // one reciprocal per pivot (a division is ~20 instructions and 80 cycles)
+    rD[j] = rd;
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = A[i][j];
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * D[k];
-      L[i][j] = s / d;
+      L[i][j] = s * rd;
     }
   }
   double y[6];
@@ -806,7 +949,7 @@ __device__ bool ldlt_solve6(const double (&A)[6][6], const double (&b)[6], doubl
 #pragma unroll
     for (int k = 0; k < i; ++k) s -= L[i][k] * y[k]; y[i] = s; }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) y[i] /= D[i];
+  for (int i = 0; i < 6; ++i) y[i] *= rD[i];
 #pragma unroll
   for (int i = 5; i >= 0; --i) { double s = y[i];
 #pragma unroll
@@ -816,66 +959,120 @@ __device__ bool ldlt_solve6(const double (&A)[6][6], const double (&b)[6], doubl
 
 struct LmState { double scale[6]; double jtj[6][6]; double g[6]; double cost, gmax; };
 
-// tiny_solver.h:166-195 (Update)
-__device__ void lm_update(const double x[6], const double pt[3], double u, double v, double wxx,
-                          double wxy, double wyy, const Cam& cam, bool active, bool first, LmState& S) {
-  double r[2], J[2][6];
-  residual_lane(x, pt, u, v, wxx, wxy, wyy, cam, active, r, J);
-  r[0] = -r[0]; r[1] = -r[1];
+// One evaluation of the cost at x: residuals and Jacobian of every point, and the 28 sums over the points that
+// everything else is made of.  `red` = (LM_ROWS * TSTRIDE + LM_SUMS) doubles of this warp's shared memory.
+// Rows 0..5 / 7..12 of the table: d r0 / d x_k and d r1 / d x_k of the lane's point, rows 6 / 13: -r0, -r1; the pair
+// sums (a <= b < 7) of  row_a . row_b + row_{7+a} . row_{7+b}  are J^T J (21), the gradient J^T (-r) (6) and
+// |r|^2 (1), unscaled; e[a * 7 - a (a - 1) / 2 + (b - a)] = sum (a, b).
+__device__ __forceinline__ void lm_eval(const double x[6], const double pt[3], double u, double v, double wxx,
+                                        double wxy, double wyy, const Cam& cam, bool active,
+                                        double (&e)[LM_SUMS], double* red, int lane) {
+  {
+    double r[2], J[2][6];
+    residual_lane(x, pt, u, v, wxx, wxy, wyy, cam, active, r, J);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { red[k * TSTRIDE + lane] = J[0][k]; red[(7 + k) * TSTRIDE + lane] = J[1][k]; }
+    red[6 * TSTRIDE + lane] = -r[0];
+    red[13 * TSTRIDE + lane] = -r[1];
+  }
+  POSE_PHASE(26);
+  const int np = 32 - __clz(__ballot_sync(FULL, active));
+  __syncwarp();
+  if (lane < LM_SUMS) {
+    int a = 0, rem = lane;
+    while (rem >= 7 - a) { rem -= 7 - a; ++a; }
+    const double* xa = red + a * TSTRIDE;
+    const double* xb = red + (a + rem) * TSTRIDE;
+    red[LM_ROWS * TSTRIDE + lane] =
+        sum_points(np, [&](int p) { return fma(xa[p], xb[p], xa[7 * TSTRIDE + p] * xb[7 * TSTRIDE + p]); });
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < LM_SUMS; ++i) e[i] = red[LM_ROWS * TSTRIDE + i];
+  __syncwarp();                      // the table is rewritten by the next evaluation
+  POSE_PHASE(27);
+}
+
+// tiny_solver.h:166-195 (Update) from the sums of lm_eval.  The Jacobi column scaling is applied to the sums,
+// (J^T J)_ab s_a s_b, instead of to J first: same numbers up to rounding, and the unscaled diagonal that defines
+// the scale on the first call comes out of the same pass.
+__device__ __forceinline__ void lm_accept(const double (&e)[LM_SUMS], bool first, LmState& S) {
+  auto at = [&](int a, int b) -> double { return e[a * 7 - a * (a - 1) / 2 + (b - a)]; };
   if (first) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) S.scale[k] = 1.0 / (1.0 + sqrt(warp_sum(J[0][k] * J[0][k] + J[1][k] * J[1][k])));
+    for (int k = 0; k < 6; ++k) S.scale[k] = 1.0 / (1.0 + sqrt(at(k, k)));
   }
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { J[0][k] *= S.scale[k]; J[1][k] *= S.scale[k]; }
   S.gmax = 0.0;
 #pragma unroll
   for (int a = 0; a < 6; ++a) {
 #pragma unroll
     for (int b = a; b < 6; ++b) {
-      const double s = warp_sum(J[0][a] * J[0][b] + J[1][a] * J[1][b]);
-      S.jtj[a][b] = s; S.jtj[b][a] = s;
+      const double sab = at(a, b) * (S.scale[a] * S.scale[b]);
+      S.jtj[a][b] = sab; S.jtj[b][a] = sab;
     }
-    const double gg = warp_sum(J[0][a] * r[0] + J[1][a] * r[1]);
+    const double gg = at(a, 6) * S.scale[a];
     S.g[a] = gg; S.gmax = fmax(S.gmax, fabs(gg));
   }
-  S.cost = 0.5 * warp_sum(r[0] * r[0] + r[1] * r[1]);
+  S.cost = 0.5 * at(6, 6);
 }
 
 // tiny_solver.h:197-293 (Solve).  Returns TinySolver's status (0 gradient, 1 step, 2 cost, 3 max-iter).
+// TinySolver evaluates the residuals at the trial point and, when the step is accepted, evaluates residuals AND
+// Jacobian at the same point again (Update).  Here the trial point gets one full evaluation whose sums serve both
+// the acceptance test (|r|^2 is one of them) and the next iteration, and that evaluation exists once in the
+// machine code (it is most of the solver).  The sequence of tests and the iteration count are TinySolver's.
 __device__ int lm_solve(double x[6], const double pt[3], double u, double v, double wxx, double wxy,
-                        double wyy, const Cam& cam, bool active, int* iterations, double* final_cost) {
+                        double wyy, const Cam& cam, bool active, int* iterations, double* final_cost,
+                        double* red, int lane) {
   LmState S;
   int status = 3, it = 0;
-  lm_update(x, pt, u, v, wxx, wxy, wyy, cam, active, true, S);
-  if (S.gmax < 1e-10) status = 0;
-  else if (S.cost < DBL_EPSILON) status = 2;
-  else {
-    double uu = 1.0 / 1e4, vv = 2.0;
-    for (it = 1; it < 50; ++it) {
-      double A[6][6], step[6], dx[6], xn[6];
+  double uu = 1.0 / 1e4, vv = 2.0, model = 1.0;
+  double xe[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) xe[i] = x[i];
+  bool first = true;
+#pragma unroll 1
+  for (;;) {
+    double e[LM_SUMS];
+    lm_eval(xe, pt, u, v, wxx, wxy, wyy, cam, active, e, red, lane);
+    const double rho = first ? 1.0 : (2 * S.cost - e[LM_SUMS - 1]) / model;
+    POSE_PHASE(15);
+    if (rho > 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = xe[i];
+      lm_accept(e, first, S);
+      POSE_PHASE(13);
+      if (S.gmax < 1e-10) { status = 0; break; }
+      if (S.cost < DBL_EPSILON) { status = 2; break; }
+      if (!first) {
+        const double tmp = 2 * rho - 1;
+        uu = uu * fmax(1 / 3., 1 - tmp * tmp * tmp);
+        vv = 2;
+      }
+      first = false;
+    } else {
+      uu *= vv; vv *= 2;
+    }
+    // next trial point from the accepted state; a failed factorisation counts as a rejected step
+    bool have_trial = false;
+#pragma unroll 1
+    while (!have_trial && ++it < 50) {
+      double A[6][6], step[6], dx[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) A[i][j] = S.jtj[i][j];
-        const double dg = fmin(fmax(S.jtj[i][i], 1e-6), 1e32);
-        const double lm = sqrt(uu * dg);
-        A[i][i] += lm * lm;
+        A[i][i] += uu * fmin(fmax(S.jtj[i][i], 1e-6), 1e32);     // (sqrt(u d))^2 in TinySolver
       }
       const bool ok = ldlt_solve6(A, S.g, step);
       double nx = 0, ndx = 0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) { dx[i] = S.scale[i] * step[i]; nx += x[i] * x[i]; ndx += dx[i] * dx[i]; }
       if (ok && sqrt(ndx) < 1e-8 * (sqrt(nx) + 1e-8)) { status = 1; break; }
-      double rho = -1.0;
       if (ok) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) xn[i] = x[i] + dx[i];
-        double r[2];
-        residual_lane(xn, pt, u, v, wxx, wxy, wyy, cam, active, r, nullptr);
-        const double f2 = warp_sum(r[0] * r[0] + r[1] * r[1]);
-        const double cost_change = 2 * S.cost - f2;
-        double model = 0;
+        for (int i = 0; i < 6; ++i) xe[i] = x[i] + dx[i];
+        model = 0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
           double s = 2 * S.g[a];
@@ -883,21 +1080,13 @@ __device__ int lm_solve(double x[6], const double pt[3], double u, double v, dou
           for (int b = 0; b < 6; ++b) s -= S.jtj[a][b] * step[b];
           model += step[a] * s;
         }
-        rho = cost_change / model;
+        have_trial = true;
+      } else {
+        uu *= vv; vv *= 2;
       }
-      if (rho > 0) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] = xn[i];
-        lm_update(x, pt, u, v, wxx, wxy, wyy, cam, active, false, S);
-        if (S.gmax < 1e-10) { status = 0; break; }
-        if (S.cost < DBL_EPSILON) { status = 2; break; }
-        const double tmp = 2 * rho - 1;
-        uu = uu * fmax(1 / 3., 1 - tmp * tmp * tmp);
-        vv = 2;
-        continue;
-      }
-      uu *= vv; vv *= 2;
     }
+    POSE_PHASE(14);
+    if (!have_trial) break;   // a converged step (status 1) or the iteration limit (status 3)
   }
   if (iterations) *iterations = it;
   if (final_cost) *final_cost = S.cost;
@@ -955,6 +1144,7 @@ lm_kernel(const double* __restrict__ p2d, const double* __restrict__ p3d, int p3
           const double* __restrict__ w2d, const double* __restrict__ K, int K_batched,
           const double* __restrict__ init_rt, const int32_t* __restrict__ npts, int B, int n_max,
           double* __restrict__ result_rt, int32_t* __restrict__ iters, double* __restrict__ final_cost) {
+  __shared__ double s_red[POSE_WARPS][LM_ROWS * TSTRIDE + LM_SUMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int img = blockIdx.x * (blockDim.x >> 5) + warp;
   if (img >= B) return;
@@ -973,7 +1163,7 @@ lm_kernel(const double* __restrict__ p2d, const double* __restrict__ p3d, int p3
 #pragma unroll
   for (int k = 0; k < 6; ++k) x[k] = init_rt[(size_t)img * 6 + k];
   int it = 0; double fc = 0;
-  lm_solve(x, pt, u, v, wxx, wxy, wyy, cam, active, &it, &fc);
+  lm_solve(x, pt, u, v, wxx, wxy, wyy, cam, active, &it, &fc, s_red[warp], lane);
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) result_rt[(size_t)img * 6 + k] = x[k];
@@ -1227,6 +1417,7 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0: RANSAC bookkeeping + LM; all: candidates
   const int img = blockIdx.x;
   if (img >= B) return;
+  POSE_PHASE_START();
   WarpScratch& ws = scratch[warp];
   // --- keypoint selection (val.py:172-177): large_k = max(#(maxval > 0.8), 24), top large_k by maxval
   const bool have = lane < K;
@@ -1264,9 +1455,11 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   const double pwf[3] = {round_f32(pt[0]), round_f32(pt[1]), round_f32(pt[2])};
   PoseRT init;
   unsigned mask = 0;
+  POSE_PHASE(0);
   const int st = pnp_ransac_epnp<W>(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask, warp,
                                     &s_ransac);
   if (warp != 0) return;
+  POSE_PHASE(11);
   double x[6];
   if (st == EPB_POSE_OK) {
     matrix_to_rodrigues(init.R, x);
@@ -1279,7 +1472,9 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
     // cpnp_m's weighting is not recoverable (binary and source absent): maxval itself (1, the documented
     // assumption), sqrt(maxval) (2) or unit weights (0 = cpnp)
     const double ww = weighted == 1 ? w : (weighted == 2 ? sqrt(fmax(w, 0.0)) : 1.0);
-    lm_solve(x, pt, u, v, ww, 0.0, ww, cam, active, nullptr, nullptr);
+    POSE_PHASE(12);
+    lm_solve(x, pt, u, v, ww, 0.0, ww, cam, active, nullptr, nullptr, ws.flat(), lane);
+    POSE_PHASE(16);
   } else {
     for (int k = 0; k < 6; ++k) x[k] = NAN;
     if (epnp_rt34 && lane == 0) for (int i = 0; i < 12; ++i) epnp_rt34[12 * (size_t)img + i] = NAN;
@@ -1296,6 +1491,7 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
     }
     if (status) status[img] = st;
   }
+  POSE_PHASE(17);
 }
 
 // demo.py:295-310
@@ -1437,3 +1633,13 @@ extern "C" int epb_esa_score(const float* pose7_pred, const float* pose7_gt, int
   esa_score_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pose7_pred, pose7_gt, B, score_t, score_r);
   return check_launch();
 }
+
+#ifdef EPB_TUNING
+// tuning build only: read and clear the phase clocks of CTA 0 (see POSE_PHASE)
+extern "C" int epb_debug_pose_phase_clocks(long long* out32) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out32, epb::g_phase_clk, 32 * sizeof(long long)) != cudaSuccess) return 1;
+  long long zero[32] = {0};
+  return cudaMemcpyToSymbol(epb::g_phase_clk, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

@@ -200,27 +200,22 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
   __syncwarp();
   double off_prev = INFINITY;
   for (int sweep = 0; sweep < 30; ++sweep) {
-    // Convergence is quadratic and never there before the fourth sweep on a full matrix; the first three tests
-    // are skipped unless the matrix arrives (nearly) diagonal, which the cheap test of sweep 0 covers.
-    if (sweep == 0 || sweep >= 4) {
-      double off = 0.0, tr = 0.0, dmin = INFINITY;
+    // Convergence is quadratic and never there before the fourth sweep on a full matrix, so the first tests are
+    // skipped (an input that is already diagonal just rotates by the identity for four sweeps).
+    if (sweep >= 4) {
+      double off = 0.0, tr = 0.0;
       for (int e = lane; e < 144; e += 32) {
         const int r = e / 12, c = e - 12 * r;
         const double v = ws.A[r][c];
-        if (r == c) { tr += fabs(v); dmin = fmin(dmin, fabs(v)); } else off += v * v;
+        if (r == c) tr += fabs(v); else off += v * v;
       }
       off = 0.5 * warp_sum(off);
       tr = warp_sum(tr);
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) dmin = fmin(dmin, __shfl_xor_sync(FULL, dmin, m));
-      // stop once every off-diagonal element is negligible against the SMALLEST eigenvalue (the null-space vectors
-      // are what EPnP needs); exact null spaces fall through to the absolute test
-      if (off < 1e-280 || off < 1e-36 * dmin * dmin) break;
       // rounding floor of an exact similarity: (12 eps tr)^2 ~ 2e-30 tr^2.  The sweeps converge quadratically
       // (off / tr^2: ... 1e-10, 1e-19, 1e-33 on this problem family), so the first sweep that lands below 1e-28 is
       // the last useful one -- the register version ran one more to SEE the stagnation.  That test stays as the
-      // fallback.
-      if (off < 1e-28 * tr * tr) break;
+      // fallback (and `!(off > 0)` ends exact and non-finite cases).
+      if (!(off > 1e-280) || off < 1e-28 * tr * tr) break;
       if (off < 1e-24 * tr * tr && off > 0.5 * off_prev) break;
       off_prev = off;
     }
@@ -228,12 +223,33 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
 #ifdef EPB_TUNING
     if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[23] += 1;
 #endif
+    // schedule entries of round 0 (each round fetches the next one's while it works)
+    int pq_own = ws.rr[0][min(lane, 5)], pq_I = ws.rr[0][bI], pq_J = ws.rr[0][bJ];
+    int pq_v[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) pq_v[m] = ws.rr[0][vJ[m]];
 #pragma unroll 1
     for (int step = 0; step < 11; ++step) {
-      const unsigned short* rr = ws.rr[step];
+      // Everything a lane will touch in this round is loaded up front -- the three pivot elements (lanes 0..5), the
+      // lane's 2x2 block of A and its element pairs of V -- so that only the (c, s) round trip through shared
+      // memory sits between the rotation parameters and the updates.
+      const int pI = pq_I & 0xff, qI = pq_I >> 8, pJ = pq_J & 0xff, qJ = pq_J >> 8;
+      const int po = pq_own & 0xff, qo = pq_own >> 8;
+      int pv[3], qv[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) { pv[m] = pq_v[m] & 0xff; qv[m] = pq_v[m] >> 8; }
+      const double app = ws.A[po][po], aqq = ws.A[qo][qo], apq = ws.A[po][qo];
+      const double b00 = ws.A[pI][pJ], b01 = ws.A[pI][qJ], b10 = ws.A[qI][pJ], b11 = ws.A[qI][qJ];
+      double vp[3], vq[3];
+#pragma unroll
+      for (int m = 0; m < 3; ++m) { vp[m] = ws.V[vr[m]][pv[m]]; vq[m] = ws.V[vr[m]][qv[m]]; }
+      {
+        const unsigned short* nx = ws.rr[step < 10 ? step + 1 : 0];
+        pq_own = nx[min(lane, 5)]; pq_I = nx[bI]; pq_J = nx[bJ];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) pq_v[m] = nx[vJ[m]];
+      }
       if (lane < 6) {
-        const int pq = rr[lane], p = pq & 0xff, q = pq >> 8;
-        const double app = ws.A[p][p], aqq = ws.A[q][q], apq = ws.A[p][q];
         // Rotation that annihilates a_pq: t = tan(theta) is the small root of  b t^2 + 2 a t - b = 0  with
         // a = (aqq - app)/2, b = a_pq, i.e. t = sgn(a) b / (|a| + h), h = hypot(a, b), and from it
         //   c^2 = (h + |a|) / (2 h),   s = sgn(a) b / (2 h c).
@@ -258,21 +274,10 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
       __syncwarp();
       POSE_PHASE(21);
       {
-        // all loads first, then the arithmetic, then the stores: the compiler cannot know that the items of a lane
-        // never alias and would otherwise run them one after the other, each waiting on its own loads
-        const int pqI = rr[bI], pqJ = rr[bJ];
-        const int pI = pqI & 0xff, qI = pqI >> 8, pJ = pqJ & 0xff, qJ = pqJ >> 8;
-        int pv[3], qv[3];
-#pragma unroll
-        for (int m = 0; m < 3; ++m) { const int pq = rr[vJ[m]]; pv[m] = pq & 0xff; qv[m] = pq >> 8; }
         const double cI = cs[2 * bI], sI = cs[2 * bI + 1], cJ = cs[2 * bJ], sJ = cs[2 * bJ + 1];
-        const double b00 = ws.A[pI][pJ], b01 = ws.A[pI][qJ], b10 = ws.A[qI][pJ], b11 = ws.A[qI][qJ];
-        double cv[3], sv[3], vp[3], vq[3];
+        double cv[3], sv[3];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          cv[m] = cs[2 * vJ[m]]; sv[m] = cs[2 * vJ[m] + 1];
-          vp[m] = ws.V[vr[m]][pv[m]]; vq[m] = ws.V[vr[m]][qv[m]];
-        }
+        for (int m = 0; m < 3; ++m) { cv[m] = cs[2 * vJ[m]]; sv[m] = cs[2 * vJ[m] + 1]; }
         // columns: [col_p, col_q] <- [c col_p - s col_q, s col_p + c col_q]; rows likewise with the row pair's (c, s)
         const double t00 = fma(cJ, b00, -sJ * b01), t01 = fma(sJ, b00, cJ * b01);
         const double t10 = fma(cJ, b10, -sJ * b11), t11 = fma(sJ, b10, cJ * b11);
@@ -681,47 +686,78 @@ __device__ int ransac_update_num_iters(double p, double ep, int model_points, in
 
 // cv2.solvePnPRansac(flags=EPNP) restated (oracle/epnp_port.py solve_pnp_ransac_epnp).
 // pw/u/v are this lane's correspondence (already rounded to float32 by the caller, as
-// OpenCV converts its inputs to CV_32F).  Returns status; all lanes of warp 0 hold the result.
+// OpenCV converts its inputs to CV_32F).  Returns status; all lanes of warp 0 (of CTA 0 of the frame) hold the result.
 //
-// W warps per image (CTA = 32 W threads), W in {2, 4, 8}.  OpenCV's loop is sequential -- iteration k draws its
-// 5-point sample from cv::RNG, solves, scores, and a better consensus shortens `niters` -- but the SAMPLES do not
-// depend on the data: every warp runs the same generator and knows the sample of every iteration.  So the
-// iterations are evaluated W at a time, one per warp, and the sequential bookkeeping (strictly-better consensus,
-// niters update, stop) is then REPLAYED in iteration order over the W results by every warp identically.  A result
-// beyond the shortened niters is ignored, exactly as if it had never been computed: the consensus set equals
-// OpenCV's for every input, while one outlier in 11 points costs one round instead of ~5 serial solves and the
-// no-consensus case ceil(100 / W) rounds instead of 100.
+// W warps per CTA and C CTAs (a thread-block cluster) per image, W * C in {2, 4, 8} candidate slots.  OpenCV's loop
+// is sequential -- iteration k draws its 5-point sample from cv::RNG, solves, scores, and a better consensus
+// shortens `niters` -- but the SAMPLES do not depend on the data: every warp runs the same generator and knows the
+// sample of every iteration.  So the iterations are evaluated W * C at a time, one per warp, and the sequential
+// bookkeeping (strictly-better consensus, niters update, stop) is then REPLAYED in iteration order over the results
+// by every warp identically.  A result beyond the shortened niters is ignored, exactly as if it had never been
+// computed: the consensus set equals OpenCV's for every input, while one outlier in 11 points costs one round
+// instead of ~5 serial solves and the no-consensus case ceil(100 / (W C)) rounds instead of 100.
 // Round 0 keeps the round-1 trick: OpenCV ends with one EPnP over the consensus set; on clean frames that set is
 // "all points" and is known only after the first sample has been solved and scored, so warp 1 solves EPnP over
-// ALL points speculatively during round 0 (the other warps take iterations 0, 1, ..., W - 2) and warp 0 takes
-// its result when the consensus turns out to be everything.  Every warp executes the same barriers.
+// ALL points speculatively during round 0 and warp 0 takes its result when the consensus turns out to be everything.
+//
+// Why clusters (round 2): one warp alone is bound by what a single warp can issue (3-4 cycles per instruction,
+// ~7 per shared-memory access: tools/micro/warp_issue.cu), and two solver warps on one SM sub-partition share its
+// FP64 and shared-memory pipes and each run at about half speed.  A round of 8 candidates on one SM therefore took
+// twice as long as a round of 4.  While the batch leaves SMs idle (2 B <= SMs) a frame gets a cluster of two CTAs
+// of four warps -- one warp per sub-partition on two SMs -- and the eight candidates of a round run at full speed;
+// the per-slot results are written into both CTAs' shared memory (DSMEM) and one cluster barrier per round
+// publishes them (the slots are double-buffered by round parity).
 struct RansacShared {
-  PoseRT spec;          // EPnP over all points (warp 1, round 0)
-  int cnt[8];           // per slot: consensus size of the candidate, -1 = not evaluated / non-finite model
-  unsigned mask[8];
+  PoseRT spec;          // EPnP over all points (warp 1 of CTA 0, round 0)
+  int cnt[2][8];        // [round parity][slot]: consensus size of the candidate, -1 = not evaluated / non-finite model
+  unsigned mask[2][8];
 };
 
-template <int W>
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// store to the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ void st_cluster_u32(void* local, unsigned rank, unsigned v) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
+template <int C>
+__device__ __forceinline__ void frame_barrier() {
+  if (C == 1) {
+    __syncthreads();
+  } else {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+}
+
+template <int W, int C>
 __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw[3], double u, double v,
                                const Cam& cam, double reproj_err, int max_iters, double confidence,
                                PoseRT& out, unsigned& inlier_mask, int warp, RansacShared* sh) {
-  static_assert(W >= 2 && W <= 8, "slots of RansacShared");
+  constexpr int WT = W * C;                          // candidate slots per round
+  static_assert(WT >= 2 && WT <= 8 && (C == 1 || C == 2), "slots of RansacShared");
+  const int rank = C == 1 ? 0 : (int)cluster_cta_rank();
+  const int gw = rank * W + warp;                    // warp index within the frame
   const int model_points = 5;
   inlier_mask = 0;
-  if (n < model_points) return EPB_POSE_TOO_FEW;   // (uniform over the CTA: no barrier has been executed)
+  if (n < model_points) return EPB_POSE_TOO_FEW;   // (uniform over the frame's CTAs: no barrier has been executed)
   // a non-finite correspondence (decode's NaN-is-max policy hands a NaN keypoint on) fails the frame as a whole
-  // instead of silently becoming an outlier: NaN pose, EPB_POSE_FAILED (uniform over the CTA as well)
+  // instead of silently becoming an outlier: NaN pose, EPB_POSE_FAILED (uniform over the frame as well)
   if (__any_sync(FULL, lane < n && !(isfinite(pw[0]) && isfinite(pw[1]) && isfinite(pw[2]) && isfinite(u) && isfinite(v))))
     return EPB_POSE_FAILED;
   const unsigned all = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
   if (n == model_points) {       // the minimal sample is the whole set: OpenCV solves it once
-    if (warp == 1) {
+    if (gw == 1) {
       PoseRT sp;
       epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
       if (lane == 0) sh->spec = sp;
     }
-    __syncthreads();
-    out = sh->spec;
+    frame_barrier<C>();
+    out = sh->spec;              // (meaningful in CTA 0, which is where warp 0 lives)
     inlier_mask = all;
     return EPB_POSE_OK;
   }
@@ -732,17 +768,19 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   const float thr2 = (float)(reproj_err * reproj_err);
   int it0 = 0;                                       // iterations replayed so far
   for (int round = 0; it0 < niters; ++round) {
-    // Round 0 is what a clean frame pays: at most four warps work in it (one per scheduler: the critical warps 0
-    // and 1 do not share issue slots), warp 1 on the speculative solve; warps 4.. join from round 1 on.
+    // Round 0 is what a clean frame pays: at most four warps per CTA work in it (one per scheduler: the critical
+    // warps 0 and 1 do not share issue slots), warp 1 on the speculative solve; the others join from round 1 on.
 #ifdef EPB_TUNING
     const int W0 = min(W, max(2, c_ransac_round0_warps));
 #else
     constexpr int W0 = W < 4 ? W : 4;
 #endif
-    const int slots = round == 0 ? W0 - 1 : W;
-    const int my_slot = round == 0 ? (warp == 0 ? 0 : warp - 1) : warp;
-    const bool speculative = round == 0 && warp == 1;
+    const int g0 = rank * W0 + warp;                 // index among the warps of round 0
+    const int slots = round == 0 ? W0 * C - 1 : WT;
+    const int my_slot = round == 0 ? (g0 == 0 ? 0 : g0 - 1) : gw;
+    const bool speculative = round == 0 && gw == 1;
     const bool idle = round == 0 && warp >= W0;
+    const int par = round & 1;
     // advance the generator through the round; keep the sample of this warp's iteration
     int idx0 = 0;
     unsigned my_m = 0;
@@ -783,25 +821,35 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
           cnt = __popc(gm);
         }
       }
-      if (lane == 0 && !idle) { sh->cnt[my_slot] = cnt; sh->mask[my_slot] = gm; }
+      if (lane == 0 && !idle) {
+        if (C == 1) {
+          sh->cnt[par][my_slot] = cnt; sh->mask[par][my_slot] = gm;
+        } else {
+#pragma unroll
+          for (int r = 0; r < C; ++r) {
+            st_cluster_u32(&sh->cnt[par][my_slot], r, (unsigned)cnt);
+            st_cluster_u32(&sh->mask[par][my_slot], r, gm);
+          }
+        }
+      }
     }
-    __syncthreads();
-    // replay OpenCV's sequential bookkeeping over the round (identical in every warp)
+    frame_barrier<C>();
+    // replay OpenCV's sequential bookkeeping over the round (identical in every warp); the next round writes the
+    // other parity, and the one after that is separated from these reads by the next barrier
     for (int sl = 0; sl < slots && it0 + sl < niters; ++sl) {
-      const int cnt = sh->cnt[sl];
+      const int cnt = sh->cnt[par][sl];
       if (cnt > max(best_count, model_points - 1)) {
-        best_mask = sh->mask[sl]; best_count = cnt;
+        best_mask = sh->mask[par][sl]; best_count = cnt;
         niters = ransac_update_num_iters(confidence, (double)(n - cnt) / n, model_points, niters);
       }
     }
     it0 += slots;
-    __syncthreads();      // the slots are rewritten by the next round
   }
   if (max_iters <= 0) {   // (no round ran: the speculative result does not exist either)
     return EPB_POSE_FAILED;
   }
   if (best_mask == 0) return EPB_POSE_FAILED;
-  if (warp != 0) return EPB_POSE_OK;                 // only warp 0 carries the pose on
+  if (gw != 0) return EPB_POSE_OK;                   // only warp 0 carries the pose on
   if (best_mask == all) out = sh->spec;              // == epnp_core over all points, first_lane 0
   else epnp_core(ws, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
   inlier_mask = best_mask;
@@ -1100,8 +1148,8 @@ __device__ __forceinline__ Cam load_cam(const double* K, int batched, int img) {
 }
 __device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
 
-template <int W>
-__global__ void __launch_bounds__(32 * W)
+template <int W, int C>
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(32 * W)
 pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __restrict__ p2d,
            const double* __restrict__ K, int K_batched, const int32_t* __restrict__ npts, int B,
            int n_max, double reproj_err, int max_iters, double confidence, double* __restrict__ rt34,
@@ -1109,7 +1157,8 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
   __shared__ WarpScratch scratch[W];
   __shared__ RansacShared s_ransac;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0 carries the result; all evaluate candidates
-  const int img = blockIdx.x;
+  const int img = blockIdx.x / C;                                // C CTAs (one cluster) per image
+  const bool lead = warp == 0 && (C == 1 || blockIdx.x % C == 0);
   if (img >= B) return;
   WarpScratch& ws = scratch[warp];
   const int n = npts ? min(npts[img], n_max) : n_max;
@@ -1124,9 +1173,9 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
   const Cam cam = load_cam(K, K_batched, img);
   PoseRT out;
   unsigned mask = 0;
-  const int st = pnp_ransac_epnp<W>(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
-                                    &s_ransac);
-  if (warp == 0 && lane == 0) {
+  const int st = pnp_ransac_epnp<W, C>(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
+                                       &s_ransac);
+  if (lead && lane == 0) {
     double* o = rt34 + (size_t)img * 12;
     if (st == EPB_POSE_OK) {
 #pragma unroll
@@ -1403,8 +1452,8 @@ __global__ void cov_to_weights_kernel(const float* __restrict__ cov, int n, int 
 }
 
 // val.py:172-228 for a batch: one warp per frame, lane k <-> keypoint k (K <= 32)
-template <int W>
-__global__ void __launch_bounds__(32 * W)
+template <int W, int C>
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(32 * W)
 pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ maxvals,
                      const double* __restrict__ bbox_xy, const double* __restrict__ rate,
                      const double* __restrict__ p3d_model, const double* __restrict__ Kmat, int B, int K,
@@ -1415,7 +1464,8 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   __shared__ RansacShared s_ransac;
   __shared__ double s_pts[W][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order (one copy per warp: no barrier needed)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0: RANSAC bookkeeping + LM; all: candidates
-  const int img = blockIdx.x;
+  const int img = blockIdx.x / C;                                // C CTAs (one cluster) per image
+  const bool lead = warp == 0 && (C == 1 || blockIdx.x % C == 0);
   if (img >= B) return;
   POSE_PHASE_START();
   WarpScratch& ws = scratch[warp];
@@ -1456,9 +1506,9 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   PoseRT init;
   unsigned mask = 0;
   POSE_PHASE(0);
-  const int st = pnp_ransac_epnp<W>(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask, warp,
-                                    &s_ransac);
-  if (warp != 0) return;
+  const int st = pnp_ransac_epnp<W, C>(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask,
+                                       warp, &s_ransac);
+  if (!lead) return;
   POSE_PHASE(11);
   double x[6];
   if (st == EPB_POSE_OK) {
@@ -1530,15 +1580,20 @@ static inline int ransac_warps(int B) {
   const int sms = device_sm_count();
   return B <= sms ? 8 : (B <= 2 * sms ? 4 : 2);
 }
+// ... and while two SMs per image are to be had, the eight warps are a cluster of two CTAs of four (one warp per
+// SM sub-partition: see pnp_ransac_epnp)
+static inline bool ransac_cluster(int B) { return 2 * B <= device_sm_count(); }
 
 static void pose_kernel_attributes() {
 #ifdef EPB_TUNING
   { const int r0 = tuning_int("EPB_RANSAC_R0", 4); cudaMemcpyToSymbol(c_ransac_round0_warps, &r0, sizeof(int)); }
 #endif
-  prefer_max_shared(pnp_kernel<2>); prefer_max_shared(pnp_kernel<4>); prefer_max_shared(pnp_kernel<8>);
+  prefer_max_shared(pnp_kernel<2, 1>); prefer_max_shared(pnp_kernel<4, 1>); prefer_max_shared(pnp_kernel<8, 1>);
+  prefer_max_shared(pnp_kernel<4, 2>); prefer_max_shared(pose_pipeline_kernel<4, 2>);
   prefer_max_shared(lm_kernel); prefer_max_shared(pose_pack_kernel);
   prefer_max_shared(rt34_to_rt6_kernel); prefer_max_shared(cov_to_weights_kernel);
-  prefer_max_shared(pose_pipeline_kernel<2>); prefer_max_shared(pose_pipeline_kernel<4>); prefer_max_shared(pose_pipeline_kernel<8>);
+  prefer_max_shared(pose_pipeline_kernel<2, 1>); prefer_max_shared(pose_pipeline_kernel<4, 1>);
+  prefer_max_shared(pose_pipeline_kernel<8, 1>);
   prefer_max_shared(esa_score_kernel);
   cudaGetLastError();
 }
@@ -1553,9 +1608,10 @@ extern "C" int epb_pnp_epnp_ransac(const double* p3d, int p3d_batched, const dou
   // W warps per image evaluate RANSAC candidates side by side (pnp_ransac_epnp): 8 while every image still gets
   // an SM of its own, fewer when the batch has to share them
   const int W = ransac_warps(B);
-#define EPB_PNP_LAUNCH(WW) pnp_kernel<WW><<<B, 32 * WW, 0, (cudaStream_t)stream>>>(                         \
+#define EPB_PNP_LAUNCH(WW, CC) pnp_kernel<WW, CC><<<B * CC, 32 * WW, 0, (cudaStream_t)stream>>>(             \
       p3d, p3d_batched, p2d, K, K_batched, npts, B, n_max, reproj_err, max_iters, confidence, rt34, inlier_mask, status)
-  if (W == 8) EPB_PNP_LAUNCH(8); else if (W == 4) EPB_PNP_LAUNCH(4); else EPB_PNP_LAUNCH(2);
+  if (ransac_cluster(B)) EPB_PNP_LAUNCH(4, 2);
+  else if (W == 8) EPB_PNP_LAUNCH(8, 1); else if (W == 4) EPB_PNP_LAUNCH(4, 1); else EPB_PNP_LAUNCH(2, 1);
 #undef EPB_PNP_LAUNCH
   return check_launch();
 }
@@ -1618,9 +1674,10 @@ extern "C" int epb_pose_pipeline(const float* preds, const float* maxvals, const
   if (B == 0) return EPB_OK;
   ProfScope ps(PROF_POSE, (cudaStream_t)stream);
   const int W = ransac_warps(B);
-#define EPB_POSE_LAUNCH(WW) pose_pipeline_kernel<WW><<<B, 32 * WW, 0, (cudaStream_t)stream>>>(                   \
+#define EPB_POSE_LAUNCH(WW, CC) pose_pipeline_kernel<WW, CC><<<B * CC, 32 * WW, 0, (cudaStream_t)stream>>>(       \
       preds, maxvals, bbox_xy, rate, p3d_model, Kmat, B, K, min_k, sel_thresh, weighted, pose7, rt6, epnp_rt34, status)
-  if (W == 8) EPB_POSE_LAUNCH(8); else if (W == 4) EPB_POSE_LAUNCH(4); else EPB_POSE_LAUNCH(2);
+  if (ransac_cluster(B)) EPB_POSE_LAUNCH(4, 2);
+  else if (W == 8) EPB_POSE_LAUNCH(8, 1); else if (W == 4) EPB_POSE_LAUNCH(4, 1); else EPB_POSE_LAUNCH(2, 1);
 #undef EPB_POSE_LAUNCH
   return check_launch();
 }

@@ -23,14 +23,13 @@ namespace epb {
 
 constexpr int POSE_WARPS = 4;
 
-struct WarpScratch {
+struct __align__(16) WarpScratch {
   double A[12][14];  // M^T M, destroyed by the eigen-solver (rows padded: 16-byte aligned pairs, fewer bank conflicts)
   double V[12][14];  // eigenvectors (columns)
   double S[80];      // reduced sums / scratch
   double L[6][10];
   double vs[4][12];  // the four null-space vectors, ascending eigenvalue
   int order[12];
-  unsigned short rr[11][6];   // round-robin schedule of the eigen-solver: p | q << 8 of pair k in round `step`
   // the same bytes as one flat array: transposed per-point tables of the sums below (EPnP) and of LM
   __device__ double* flat() { return reinterpret_cast<double*>(this); }
 };
@@ -158,27 +157,31 @@ __device__ __noinline__ void svd3_cv(const double a[9], double w[3], double ut[9
   }
 }
 
-// Round-robin pair (p, q) number k of round `step` for 12 indices (circle method: 11 stays, the others go round):
-// over the 11 rounds every pair of indices meets exactly once and the six pairs of a round are disjoint.
-__device__ __forceinline__ void rr_pair(int step, int k, int& p, int& q) {
-  int a = step + k; a -= a >= 11 ? 11 : 0;
-  int b = step - k; b += b < 0 ? 11 : 0;
-  p = a; q = k == 0 ? 11 : b;
-}
-
-// Parallel-order Jacobi eigen-decomposition of the symmetric 12x12 in ws.A (destroyed; eigenvalues end up on its
-// diagonal), eigenvectors in the columns of ws.V, the four of the smallest eigenvalues in ws.vs.  Both matrices
-// stay in shared memory and the warp works BY 2x2 BLOCK, not by column: a round rotates six disjoint index pairs at
-// once, A <- J^T A J, V <- V J with J = diag of six plane rotations, and under that the 2x2 block (pair I rows,
-// pair J columns) of A only mixes with itself:  B' = J_I^T B J_J.
+// Parallel-order Jacobi eigen-decomposition of the symmetric 12x12 in ws.A (destroyed), the four eigenvectors of
+// the smallest eigenvalues to ws.vs (ascending).  Both matrices stay in shared memory and the warp works BY 2x2
+// BLOCK: a round rotates the six index pairs (2k, 2k+1) at once, A <- J^T A J, V <- V J with J = diag of six plane
+// rotations, and under that the 2x2 block (pair I rows, pair J columns) of A only mixes with itself,
+// B' = J_I^T B J_J.
 //   1. lanes 0..5 compute the (c, s) of their pair from three elements of A and publish them;
-//   2. lanes 0..20 own the 21 blocks I <= J: load four elements, two small products, store them and their mirror
-//      image; then all lanes rotate the 72 (row, pair) element pairs of V, at most three each.
-// Two warp barriers and ~180 warp instructions per round, against ~500 for the register-resident version of
-// round 1 (one column per lane, rows exchanged by shuffle: 39 double shuffles, two 12-way select chains to find
-// the pivot elements and a physical tournament permutation per round) -- and this is the longest serial piece of
-// a pose: 115 k of the 238 k cycles of a clean single frame before, measured with the phase clocks.
-__device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
+//   2. lanes 0..20 own the 21 blocks I <= J (two 16-byte loads, two small products, stores of the block and of its
+//      mirror image), and all lanes rotate the 72 (row, pair) element pairs of V, at most three each.
+// So that every pair of indices meets, the contents then move by the fixed tournament permutation pi (position 0
+// stays, the others go round: all 66 pairs in 11 rounds, back in place after a sweep).  The move costs nothing: the
+// results are STORED at their permuted positions into a second copy of A and V (the two copies swap roles every
+// round), so every lane reads and writes the same static offsets in every round -- no schedule look-ups, no index
+// arithmetic.  The solve is the program of ONE warp, and one warp alone issues an instruction every 3-4 cycles and
+// a shared-memory access every ~7 (tools/micro/warp_issue.cu): what counts is instructions per round, ~120 here
+// against ~500 for the register-resident version of round 1 (one column per lane, rows exchanged by shuffle).
+// a2 = 12 x 14 doubles of scratch for the second copy of A; the second copy of V overlays ws.S[12..], ws.L and
+// ws.vs, which are all dead while the solver runs.
+__device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane, double* a2) {
+  constexpr int LD = 14;
+  // pi[x]: where the content of position x goes after a round
+  auto pi = [](int x) -> int { return (int)((0x9b7a58361420ull >> (4 * x)) & 15ull); };   // {0,2,4,1,6,3,8,5,10,7,11,9}
+  double* A0 = &ws.A[0][0];
+  double* V0 = &ws.V[0][0];
+  double* V1 = ws.S + 12;
+  static_assert(80 - 12 + 60 + 48 >= 12 * LD, "second copy of V");
   for (int e = lane; e < 144; e += 32) ws.V[e / 12][e % 12] = (e / 12 == e % 12) ? 1.0 : 0.0;
   int bI = 0, bJ = 0;                       // this lane's block of A (lanes 0..20)
   {
@@ -186,17 +189,26 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
     while (bI < 5 && rem >= 6 - bI) { rem -= 6 - bI; ++bI; }
     bJ = min(bI + rem, 5);
   }
+  // static element offsets: loads of the block rows (2 bI, 2 bI + 1) x cols (2 bJ, 2 bJ + 1), stores at pi(...)
+  const int oL0 = (2 * bI) * LD + 2 * bJ, oL1 = (2 * bI + 1) * LD + 2 * bJ;
+  const int r0 = pi(2 * bI), r1 = pi(2 * bI + 1), c0 = pi(2 * bJ), c1 = pi(2 * bJ + 1);
+  const int oS00 = r0 * LD + c0, oS01 = r0 * LD + c1, oS10 = r1 * LD + c0, oS11 = r1 * LD + c1;
+  const int oM00 = c0 * LD + r0, oM01 = c1 * LD + r0, oM10 = c0 * LD + r1, oM11 = c1 * LD + r1;   // mirror image
+  const bool hasA = lane < 21, mirror = hasA && bI != bJ;
   // this lane's (row, pair) items of V: item = lane + 32 m < 72, row = item / 6, pair = item % 6
-  int vr[3], vJ[3];
+  int vJ[3], oVL[3], oVp[3], oVq[3];
 #pragma unroll
-  for (int m = 0; m < 3; ++m) { const int item = min(lane + 32 * m, 71); vr[m] = item / 6; vJ[m] = item - 6 * vr[m]; }
-  const bool v2 = lane + 64 < 72;
-  double* cs = ws.S;                        // [6][2]: (c, s) of the six pairs of the round
-  for (int e = lane; e < 66; e += 32) {     // the schedule as a table: one 16-bit load per pair and round
-    int p, q;
-    rr_pair(e / 6, e % 6, p, q);
-    ws.rr[e / 6][e % 6] = (unsigned short)(p | (q << 8));
+  for (int m = 0; m < 3; ++m) {
+    const int item = min(lane + 32 * m, 71), vr = item / 6;
+    vJ[m] = item - 6 * vr;
+    oVL[m] = vr * LD + 2 * vJ[m];
+    oVp[m] = vr * LD + pi(2 * vJ[m]); oVq[m] = vr * LD + pi(2 * vJ[m] + 1);
   }
+  const bool v2 = lane + 64 < 72;
+  const int kp = min(lane, 5);              // pivot pair of lanes 0..5
+  const int oP0 = (2 * kp) * LD + 2 * kp, oP1 = (2 * kp + 1) * LD + 2 * kp + 1;
+  double2* cs = reinterpret_cast<double2*>(ws.S);      // [6]: (c, s) of the six pairs of the round
+  double* sA = A0; double* dA = a2; double* sV = V0; double* dV = V1;
   __syncwarp();
   double off_prev = INFINITY;
   for (int sweep = 0; sweep < 30; ++sweep) {
@@ -206,7 +218,7 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
       double off = 0.0, tr = 0.0;
       for (int e = lane; e < 144; e += 32) {
         const int r = e / 12, c = e - 12 * r;
-        const double v = ws.A[r][c];
+        const double v = sA[r * LD + c];
         if (r == c) tr += fabs(v); else off += v * v;
       }
       off = 0.5 * warp_sum(off);
@@ -223,32 +235,17 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
 #ifdef EPB_TUNING
     if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[23] += 1;
 #endif
-    // schedule entries of round 0 (each round fetches the next one's while it works)
-    int pq_own = ws.rr[0][min(lane, 5)], pq_I = ws.rr[0][bI], pq_J = ws.rr[0][bJ];
-    int pq_v[3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) pq_v[m] = ws.rr[0][vJ[m]];
 #pragma unroll 1
     for (int step = 0; step < 11; ++step) {
-      // Everything a lane will touch in this round is loaded up front -- the three pivot elements (lanes 0..5), the
-      // lane's 2x2 block of A and its element pairs of V -- so that only the (c, s) round trip through shared
-      // memory sits between the rotation parameters and the updates.
-      const int pI = pq_I & 0xff, qI = pq_I >> 8, pJ = pq_J & 0xff, qJ = pq_J >> 8;
-      const int po = pq_own & 0xff, qo = pq_own >> 8;
-      int pv[3], qv[3];
+      // everything the lane will touch is loaded up front; only the (c, s) round trip through shared memory sits
+      // between the rotation parameters and the updates
+      const double2 piv = *reinterpret_cast<const double2*>(sA + oP0);   // a_pp, a_pq
+      const double aqq = sA[oP1];
+      const double2 row0 = *reinterpret_cast<const double2*>(sA + oL0);
+      const double2 row1 = *reinterpret_cast<const double2*>(sA + oL1);
+      double2 vv[3];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) { pv[m] = pq_v[m] & 0xff; qv[m] = pq_v[m] >> 8; }
-      const double app = ws.A[po][po], aqq = ws.A[qo][qo], apq = ws.A[po][qo];
-      const double b00 = ws.A[pI][pJ], b01 = ws.A[pI][qJ], b10 = ws.A[qI][pJ], b11 = ws.A[qI][qJ];
-      double vp[3], vq[3];
-#pragma unroll
-      for (int m = 0; m < 3; ++m) { vp[m] = ws.V[vr[m]][pv[m]]; vq[m] = ws.V[vr[m]][qv[m]]; }
-      {
-        const unsigned short* nx = ws.rr[step < 10 ? step + 1 : 0];
-        pq_own = nx[min(lane, 5)]; pq_I = nx[bI]; pq_J = nx[bJ];
-#pragma unroll
-        for (int m = 0; m < 3; ++m) pq_v[m] = nx[vJ[m]];
-      }
+      for (int m = 0; m < 3; ++m) vv[m] = *reinterpret_cast<const double2*>(sV + oVL[m]);
       if (lane < 6) {
         // Rotation that annihilates a_pq: t = tan(theta) is the small root of  b t^2 + 2 a t - b = 0  with
         // a = (aqq - app)/2, b = a_pq, i.e. t = sgn(a) b / (|a| + h), h = hypot(a, b), and from it
@@ -258,6 +255,7 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
         // cycles each on this part, tools/micro/fp64_latency.cu).  c^2 + s^2 = 1 within rounding and A is
         // transformed with those very (c, s) (an exact orthogonal similarity, no "a_pq := 0" shortcut), so any
         // residual a_pq is removed by the next sweep.
+        const double app = piv.x, apq = piv.y;
         const double alpha = 0.5 * (aqq - app);
         const double h2 = fma(alpha, alpha, apq * apq);
         double c = 1.0, s = 0.0;
@@ -269,15 +267,14 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
           c = c2 * rc;
           s = alpha < 0.0 ? -(hb * rc) : hb * rc;
         }
-        cs[2 * lane] = c; cs[2 * lane + 1] = s;
+        cs[lane] = make_double2(c, s);
       }
       __syncwarp();
       POSE_PHASE(21);
       {
-        const double cI = cs[2 * bI], sI = cs[2 * bI + 1], cJ = cs[2 * bJ], sJ = cs[2 * bJ + 1];
-        double cv[3], sv[3];
-#pragma unroll
-        for (int m = 0; m < 3; ++m) { cv[m] = cs[2 * vJ[m]]; sv[m] = cs[2 * vJ[m] + 1]; }
+        const double2 csI = cs[bI], csJ = cs[bJ];
+        const double cI = csI.x, sI = csI.y, cJ = csJ.x, sJ = csJ.y;
+        const double b00 = row0.x, b01 = row0.y, b10 = row1.x, b11 = row1.y;
         // columns: [col_p, col_q] <- [c col_p - s col_q, s col_p + c col_q]; rows likewise with the row pair's (c, s)
         const double t00 = fma(cJ, b00, -sJ * b01), t01 = fma(sJ, b00, cJ * b01);
         const double t10 = fma(cJ, b10, -sJ * b11), t11 = fma(sJ, b10, cJ * b11);
@@ -285,32 +282,42 @@ __device__ __noinline__ void jacobi_eigh12(WarpScratch& ws, int lane) {
         const double n01 = fma(cI, t01, -sI * t11), n11 = fma(sI, t01, cI * t11);
         double np[3], nq[3];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) { np[m] = fma(cv[m], vp[m], -sv[m] * vq[m]); nq[m] = fma(sv[m], vp[m], cv[m] * vq[m]); }
-        if (lane < 21) {
-          ws.A[pI][pJ] = n00; ws.A[pI][qJ] = n01; ws.A[qI][pJ] = n10; ws.A[qI][qJ] = n11;
-          if (bI != bJ) { ws.A[pJ][pI] = n00; ws.A[qJ][pI] = n01; ws.A[pJ][qI] = n10; ws.A[qJ][qI] = n11; }
+        for (int m = 0; m < 3; ++m) {
+          const double2 cv = cs[vJ[m]];
+          np[m] = fma(cv.x, vv[m].x, -cv.y * vv[m].y);
+          nq[m] = fma(cv.y, vv[m].x, cv.x * vv[m].y);
         }
-        ws.V[vr[0]][pv[0]] = np[0]; ws.V[vr[0]][qv[0]] = nq[0];
-        ws.V[vr[1]][pv[1]] = np[1]; ws.V[vr[1]][qv[1]] = nq[1];
-        if (v2) { ws.V[vr[2]][pv[2]] = np[2]; ws.V[vr[2]][qv[2]] = nq[2]; }
+        if (hasA) { dA[oS00] = n00; dA[oS01] = n01; dA[oS10] = n10; dA[oS11] = n11; }
+        if (mirror) { dA[oM00] = n00; dA[oM01] = n01; dA[oM10] = n10; dA[oM11] = n11; }
+        dV[oVp[0]] = np[0]; dV[oVq[0]] = nq[0];
+        dV[oVp[1]] = np[1]; dV[oVq[1]] = nq[1];
+        if (v2) { dV[oVp[2]] = np[2]; dV[oVq[2]] = nq[2]; }
       }
       __syncwarp();
+      { double* t = sA; sA = dA; dA = t; t = sV; sV = dV; dV = t; }
       POSE_PHASE(22);
     }
   }
-  // ascending order of the eigenvalues (stable)
+  // ascending order of the eigenvalues (stable); value at position x <-> column x of V (a whole number of sweeps
+  // leaves every content at its original position)
   if (lane == 0) {
     for (int i = 0; i < 12; ++i) ws.order[i] = i;
     for (int i = 1; i < 12; ++i) {
       const int oi = ws.order[i];
-      const double wi = ws.A[oi][oi];
+      const double wi = sA[oi * LD + oi];
       int j = i - 1;
-      while (j >= 0 && ws.A[ws.order[j]][ws.order[j]] > wi) { ws.order[j + 1] = ws.order[j]; --j; }
+      while (j >= 0 && sA[ws.order[j] * LD + ws.order[j]] > wi) { ws.order[j + 1] = ws.order[j]; --j; }
       ws.order[j + 1] = oi;
     }
   }
   __syncwarp();
-  for (int e = lane; e < 48; e += 32) ws.vs[e / 12][e % 12] = ws.V[e % 12][ws.order[e / 12]];
+  // (the current copy of V may be the one that overlays ws.vs: read everything, then write)
+  const int e1 = min(lane + 32, 47);
+  const double x0 = sV[(lane % 12) * LD + ws.order[lane / 12]];
+  const double x1 = sV[(e1 % 12) * LD + ws.order[e1 / 12]];
+  __syncwarp();
+  ws.vs[lane / 12][lane % 12] = x0;
+  if (lane + 32 < 48) ws.vs[e1 / 12][e1 % 12] = x1;
   __syncwarp();
 }
 
@@ -471,7 +478,7 @@ __device__ void compute_r_and_t3(WarpScratch& ws, const double be[4], const doub
 // (one out-of-line copy: the RANSAC candidates, the speculative all-point solve and the final solve over the
 // consensus set share it, so the W = 2 / 4 / 8 instantiations of the kernels execute the SAME machine code and
 // return bit-identical poses whatever the batch size; it also takes two inlined copies out of the instruction cache)
-__device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, int n, int first_lane,
+__device__ __noinline__ void epnp_core(WarpScratch& ws, double* a2, int lane, bool active, int n, int first_lane,
                           const double pw_in[3], double u, double v, const Cam& cam, PoseRT& best) {
   double pw[3] = {active ? pw_in[0] : 0.0, active ? pw_in[1] : 0.0, active ? pw_in[2] : 0.0};
   const unsigned amask = __ballot_sync(FULL, active);
@@ -555,7 +562,7 @@ __device__ __noinline__ void epnp_core(WarpScratch& ws, int lane, bool active, i
   }
   __syncwarp();
   POSE_PHASE(3);
-  jacobi_eigh12(ws, lane);
+  jacobi_eigh12(ws, lane, a2);
   POSE_PHASE(4);
   // L_6x10 and rho
   {
@@ -735,7 +742,7 @@ __device__ __forceinline__ void frame_barrier() {
 }
 
 template <int W, int C>
-__device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw[3], double u, double v,
+__device__ int pnp_ransac_epnp(WarpScratch& ws, double* a2, int lane, int n, const double pw[3], double u, double v,
                                const Cam& cam, double reproj_err, int max_iters, double confidence,
                                PoseRT& out, unsigned& inlier_mask, int warp, RansacShared* sh) {
   constexpr int WT = W * C;                          // candidate slots per round
@@ -753,7 +760,7 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   if (n == model_points) {       // the minimal sample is the whole set: OpenCV solves it once
     if (gw == 1) {
       PoseRT sp;
-      epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
+      epnp_core(ws, a2, lane, lane < n, n, 0, pw, u, v, cam, sp);
       if (lane == 0) sh->spec = sp;
     }
     frame_barrier<C>();
@@ -798,14 +805,14 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
     }
     if (speculative) {
       PoseRT sp;
-      epnp_core(ws, lane, lane < n, n, 0, pw, u, v, cam, sp);
+      epnp_core(ws, a2, lane, lane < n, n, 0, pw, u, v, cam, sp);
       if (lane == 0) sh->spec = sp;
     } else {
       int cnt = -1;
       unsigned gm = 0;
       if (!idle && it0 + my_slot < niters) {
         PoseRT cur;
-        epnp_core(ws, lane, (my_m >> lane) & 1u, 5, idx0, pw, u, v, cam, cur);
+        epnp_core(ws, a2, lane, (my_m >> lane) & 1u, 5, idx0, pw, u, v, cam, cur);
         bool finite = true;
 #pragma unroll
         for (int i = 0; i < 9; ++i) finite = finite && isfinite(cur.R[i]);
@@ -851,7 +858,7 @@ __device__ int pnp_ransac_epnp(WarpScratch& ws, int lane, int n, const double pw
   if (best_mask == 0) return EPB_POSE_FAILED;
   if (gw != 0) return EPB_POSE_OK;                   // only warp 0 carries the pose on
   if (best_mask == all) out = sh->spec;              // == epnp_core over all points, first_lane 0
-  else epnp_core(ws, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
+  else epnp_core(ws, a2, lane, (best_mask >> lane) & 1u, best_count, __ffs(best_mask) - 1, pw, u, v, cam, out);
   inlier_mask = best_mask;
   return EPB_POSE_OK;
 }
@@ -1156,6 +1163,7 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
            unsigned long long* __restrict__ inlier_mask, int32_t* __restrict__ status) {
   __shared__ WarpScratch scratch[W];
   __shared__ RansacShared s_ransac;
+  __shared__ __align__(16) double s_a2[W][12 * 14];              // the eigen-solver's second copy of M^T M
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0 carries the result; all evaluate candidates
   const int img = blockIdx.x / C;                                // C CTAs (one cluster) per image
   const bool lead = warp == 0 && (C == 1 || blockIdx.x % C == 0);
@@ -1173,7 +1181,7 @@ pnp_kernel(const double* __restrict__ p3d, int p3d_batched, const double* __rest
   const Cam cam = load_cam(K, K_batched, img);
   PoseRT out;
   unsigned mask = 0;
-  const int st = pnp_ransac_epnp<W, C>(ws, lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
+  const int st = pnp_ransac_epnp<W, C>(ws, s_a2[warp], lane, n, pw, u, v, cam, reproj_err, max_iters, confidence, out, mask, warp,
                                        &s_ransac);
   if (lead && lane == 0) {
     double* o = rt34 + (size_t)img * 12;
@@ -1462,7 +1470,9 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
                      int32_t* __restrict__ status) {
   __shared__ WarpScratch scratch[W];
   __shared__ RansacShared s_ransac;
-  __shared__ double s_pts[W][32][6];  // x3d,y3d,z3d,u,v,maxval in rank order (one copy per warp: no barrier needed)
+  // x3d,y3d,z3d,u,v,maxval in rank order (one copy per warp: no barrier needed); once the lanes hold their point
+  // the 192 doubles serve as the eigen-solver's second copy of M^T M
+  __shared__ __align__(16) double s_pts[W][32][6];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // warp 0: RANSAC bookkeeping + LM; all: candidates
   const int img = blockIdx.x / C;                                // C CTAs (one cluster) per image
   const bool lead = warp == 0 && (C == 1 || blockIdx.x % C == 0);
@@ -1506,7 +1516,7 @@ pose_pipeline_kernel(const float* __restrict__ preds, const float* __restrict__ 
   PoseRT init;
   unsigned mask = 0;
   POSE_PHASE(0);
-  const int st = pnp_ransac_epnp<W, C>(ws, lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask,
+  const int st = pnp_ransac_epnp<W, C>(ws, &s_pts[warp][0][0], lane, n, pwf, round_f32(u), round_f32(v), cam, 5.0, 100, 0.99, init, mask,
                                        warp, &s_ransac);
   if (!lead) return;
   POSE_PHASE(11);

@@ -267,7 +267,12 @@ def pose_stress():
         k_t = torch.from_numpy(kp.astype(np.float32)).to(DEV)
         ms = timed(lambda: pipeline.poses_from_keypoints(k_t, m, K)["pose7"], 20)
         st = pipeline.poses_from_keypoints(k_t, m, K)["status"]
-        out[tag] = {"ms_per_64_frames": ms, "failed": int((st != 0).sum())}
+        # the batch ends with its slowest frame; the single-frame call times of the first 16 frames say what a
+        # typical frame of the kind costs
+        one = sorted(timed(lambda i=i: pipeline.poses_from_keypoints(k_t[i:i + 1], m, K)["pose7"], 10) * 1e3
+                     for i in range(16))
+        out[tag] = {"ms_per_64_frames": ms, "failed": int((st != 0).sum()),
+                    "single_frame_us": {"median": one[8], "max": one[-1]}}
     return out
 
 

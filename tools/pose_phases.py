@@ -18,11 +18,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-NAMES = ["select/un-crop", "epnp: centroid+cov sums", "epnp: svd3(cov)+alphas", "epnp: MtM sums+fill", "epnp: jacobi 12x12",
-         "epnp: L, rho", "epnp: 3 initial lstsq", "epnp: 5 Gauss-Newton", "crt3: pc + sums", "crt3: svd3 + R,t",
-         "crt3: scoring", "ransac: score, barriers, replay", "rodrigues", "lm: update", "lm: ldlt", "lm: trial residual",
-         "lm: exit", "pack"]
-
+NAMES = ["select/un-crop", "epnp: sampling, centroid + covariance sums", "epnp: svd3(cov) + alphas", "epnp: MtM sums + fill",
+         "epnp: eigen-solver entry/exit", "epnp: L, rho", "(unused)", "epnp: beta passes, rest", "crt3: pc + sums",
+         "crt3: svd3 + R,t", "crt3: scoring", "ransac: score, barrier, replay", "rodrigues", "lm: accept", "lm: solve + step",
+         "lm: rho", "lm: exit", "pack"]
 
 def main():
     from synth import make_pose_case, tango_model, ESA_K
@@ -58,7 +57,7 @@ def main():
     extra = {"jacobi: convergence checks": buf[20] / reps, "jacobi: rotation parameters": buf[21] / reps,
              "jacobi: block updates": buf[22] / reps, "jacobi: sweeps": buf[23] / reps,
              "gn: build a, b": buf[24] / reps, "gn: lstsq6": buf[25] / reps,
-             "lm update: residual + jets": buf[26] / reps, "lm update: table sums": buf[27] / reps}
+             "lm eval: residual + jets": buf[26] / reps, "lm eval: table sums": buf[27] / reps}
     print(json.dumps({"frames": B, "outliers": n_out, "total_cycles": tot,
                       "phases": {n: round(c) for n, c in zip(NAMES, cyc)}, "inside_jacobi": extra}))
 

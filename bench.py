@@ -539,6 +539,19 @@ def run_ours(a):
         t_e0 = time.time()
         ms_e2e = timed(step_e2e, a.steps)
     t_e1 = time.time()
+    # what the bus gives a plain cudaMemcpyAsync of the same number of bytes from pinned memory on this box: the
+    # denominator of the e2e leg's own bound (`e2e.pcie`), measured after its timed region
+    dma_gbs = None
+    if not a.no_e2e:
+        try:
+            n_pay = int(mask_np.size + int(mask_np.astype(bool).sum()) * a.vn * 8)
+            src = torch.empty(n_pay, dtype=torch.uint8).pin_memory()
+            dst = torch.empty(n_pay, dtype=torch.uint8, device=dev)
+            dma_ms = timed(lambda: dst.copy_(src, non_blocking=True), 10) / 10
+            dma_gbs = n_pay / (dma_ms * 1e-3) / 1e9
+            del src, dst
+        except Exception:
+            dma_gbs = None
     clocks = clocks_e2e = None
     if sampler:
         sampler.stop()
@@ -594,7 +607,14 @@ def run_ours(a):
                 "api": "pipeline.poses_from_vertex(pinned host mask, pinned host field, ..., host_inputs_ready=True) + pose D2H",
                 "ms_per_step": ms_e2e / a.steps, "host_input_bytes_per_step": host_bytes, "clocks": clocks_e2e, "host_numa_binding": numa,
                 "transfer": "mask cudaMemcpyAsync from pinned memory; field read zero-copy from pinned memory by the "
-                            "compaction kernel (foreground pixel groups only); poses D2H into pinned memory"},
+                            "compaction kernel (foreground pixel groups only); poses D2H into pinned memory",
+                # the e2e leg is bound by the bus, not by the kernels: bytes that must cross per step over the time of
+                # a step, against a plain pinned-memory DMA copy of the same size measured in this run
+                "pcie": None if not dma_gbs or not (ms_e2e == ms_e2e) else {
+                    "bound": "pcie", "achieved": h2d / world / (ms_e2e / a.steps * 1e-3) / 1e9, "peak": dma_gbs,
+                    "unit": "GB/s per GPU", "frac": h2d / world / (ms_e2e / a.steps * 1e-3) / 1e9 / dma_gbs,
+                    "peak_source": "cudaMemcpyAsync of one rank's h2d bytes from pinned memory, all ranks at once, "
+                                   "this run (rank 0's figure)"}},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "vote_count_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,

@@ -63,22 +63,23 @@ def test_pnp_batch_vs_cv2_with_outliers(cuda_dev):
 
 
 def test_ransac_candidates_in_parallel_equal_the_sequential_loop(cuda_dev):
-    """The kernel evaluates RANSAC iterations W at a time (W = 8, 4 or 2 warps per image, chosen by the batch size)
-    and replays OpenCV's sequential bookkeeping over the results: consensus sets and poses must equal cv2's for up
-    to 4 gross outliers in 11 points, and must not depend on W."""
+    """The kernel evaluates RANSAC iterations 8, 4 or 2 at a time (a two-CTA cluster of 4 warps each, or 8 / 4 / 2 warps
+    in one CTA per image, chosen by the batch size) and replays OpenCV's sequential bookkeeping over the results:
+    consensus sets and poses must equal cv2's for up to 4 gross outliers in 11 points, and must not depend on the
+    launch shape."""
     from esa_pose_estimation_b200 import pnp as P
     cases = [make_pose_case(7000 + i, 11, 0.6, i % 5) for i in range(40)]
     p3 = np.stack([c["p3d"] for c in cases]); p2 = np.stack([c["p2d"] for c in cases])
     K_d = torch.from_numpy(ESA_K).to(cuda_dev)
 
-    def run(reps):       # batch sizes 40 (W = 8), 280 (W = 4), 600 (W = 2) on a 148-SM part
+    def run(reps):       # batch sizes 40 (cluster 2 x 4), 120 (W = 8), 280 (W = 4), 600 (W = 2) on a 148-SM part
         a = torch.from_numpy(np.tile(p3, (reps, 1, 1))).to(cuda_dev)
         b = torch.from_numpy(np.tile(p2, (reps, 1, 1))).to(cuda_dev)
         rt, mask, status = P.pnp_batch(a, b, K_d, return_status=True)
         return rt.cpu().numpy(), mask.cpu().numpy(), status.cpu().numpy()
 
     rt8, m8, s8 = run(1)
-    for reps in (7, 15):
+    for reps in (3, 7, 15):
         rt, m, st = run(reps)
         for r in range(reps):
             sl = slice(r * 40, (r + 1) * 40)

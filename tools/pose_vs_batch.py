@@ -1,5 +1,10 @@
+#!/usr/bin/env python
+"""Pose kernel time against the batch size (launch shapes: two-CTA cluster per frame up to SMs / 2 frames, then 8, 4 and
+2 solver warps in one CTA per frame)."""
 import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests"); sys.path.insert(0, "/root/repo/tools")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for d in ("", "tests", "tools"):
+    sys.path.insert(0, os.path.join(ROOT, d))
 import numpy as np, torch
 from esa_pose_estimation_b200 import _lib
 if os.environ.get("OLDLIB"): _lib.LIB_PATH = os.environ["OLDLIB"]

@@ -1,5 +1,6 @@
 // Per-image pose solve for sm_100a: EPnP-RANSAC initialisation + Levenberg-Marquardt refinement,
-// one warp per image, one lane per 2-D/3-D correspondence (n <= 32), FP64 throughout.
+// one lane per 2-D/3-D correspondence (n <= 32), one warp per EPnP solve, 2-8 solver warps per image (RANSAC
+// candidates side by side; a two-CTA cluster per image while SMs are idle), FP64 throughout.
 //
 // Replaces (paths under /root/reference):
 //   pnp.py:46-90           pnp(): cv2.solvePnPRansac(flags=EPNP, reprojectionError=5) + Rodrigues
@@ -12,8 +13,10 @@
 // cv::RNG(-1) samples of 5, float32-rounded inputs) is the one validated on the CPU in
 // oracle/epnp_port.py; this file transliterates it.
 //
-// Latency/FP64-bound, ~360 B of traffic per pose: no tiling to speak of; the design goal is
-// to keep thousands of independent warps resident (4 warps/CTA, ~7 KB smem per CTA).
+// ~360 B of traffic per pose and ~1e5 dependent FP64 operations: nothing to tile.  A solve is the program of ONE
+// warp, and one warp alone issues an instruction every 3-4 cycles and a shared-memory access every ~7
+// (tools/micro/warp_issue.cu, fp64_latency.cu): the design counts instructions per solve, keeps MUFU / F2F /
+// divisions out of the serial chain and gives every solver warp an SM sub-partition of its own.
 #include <float.h>
 #include <math.h>
 

@@ -971,7 +971,7 @@ __device__ __forceinline__ void block_sum_d(double (&v)[N], double* smem /* [N*8
 //    ransac_voting_gpu.py:561-569 (first max, ratio = count/tn, strict '<' update from zeros)
 //    and :578-595 (re-vote the winner, 2x2 normal equations).  Sums in FP64.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 winner_refine_kernel(epb_voting_params p, Workspace ws,
                      float* __restrict__ pts, float* __restrict__ var_or_conf,
                      int32_t* __restrict__ status) {

@@ -99,6 +99,9 @@ class GraphedHeatmapPose:
         return self.out
 
 
+_unit_weights = {}
+
+
 def poses_from_keypoints(kpts, p3d_model, K, bbox_xy=None, rate=None, weights=None):
     """kpts [B,vn,2] f32 (crop px).  Unit (or given) weights; all keypoints are used."""
     b, vn = kpts.shape[0], kpts.shape[1]
@@ -108,8 +111,13 @@ def poses_from_keypoints(kpts, p3d_model, K, bbox_xy=None, rate=None, weights=No
     if rate is None:
         rate = torch.ones((b,), dtype=torch.float64, device=dev)
     weighted = weights is not None
-    if weights is None:
-        weights = torch.ones((b, vn), dtype=torch.float32, device=dev)
+    if weights is None:                      # read-only constant: one tensor per shape instead of a fill kernel per call
+        key = (dev.index, b, vn)
+        weights = _unit_weights.get(key)
+        if weights is None:
+            if len(_unit_weights) > 64:
+                _unit_weights.clear()
+            weights = _unit_weights[key] = torch.ones((b, vn), dtype=torch.float32, device=dev)
     # min_k = vn selects every keypoint (large_k = max(#(w > thresh), vn) capped at vn)
     return _pnp.pose_pipeline(kpts, weights, bbox_xy, rate, p3d_model, K, min_k=vn, sel_thresh=float("inf"),
                               weighted=weighted)

@@ -180,7 +180,7 @@ def _run(mode, mask, vertex, hn, rounds, thresh, min_num, max_num, topk=0, mean_
         io.status = _lib.ptr(out["status"])
     consumed = None
     if gen is not None:
-        consumed = torch.zeros((1,), dtype=torch.int64, device=dev)
+        consumed = torch.empty((1,), dtype=torch.int64, device=dev)   # always written by rng_offsets_kernel
         io.philox_consumed = _lib.ptr(consumed)
     io.mask, io.vertex = _lib.ptr(mask_u8), _lib.ptr(vertex)
 

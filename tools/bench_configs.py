@@ -31,15 +31,21 @@ except Exception:
 
 
 def timed(fn, steps, warmup=3):
+    import gc
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()          # like timeit: a generation-2 collection stalls the enqueueing thread for tens of ms
+    try:
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        gc.enable()
     return e0.elapsed_time(e1) / steps
 
 

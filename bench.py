@@ -586,7 +586,10 @@ def run_ours(a):
             n_pay = int(mask_np.size + int(mask_np.astype(bool).sum()) * a.vn * 8)
             src = torch.empty(n_pay, dtype=torch.uint8).pin_memory()
             dst = torch.empty(n_pay, dtype=torch.uint8, device=dev)
-            dma_ms = timed(lambda: dst.copy_(src, non_blocking=True), 10) / 10
+            src.fill_(1)                                     # touch the pages before the DMA engines do
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            dma_ms = min(timed(lambda: dst.copy_(src, non_blocking=True), 10) / 10 for _ in range(3))   # a peak: best of 3
             dma_gbs = n_pay / (dma_ms * 1e-3) / 1e9
             del src, dst
         except Exception:

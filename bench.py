@@ -335,7 +335,7 @@ def secondary_configs(a, world, rank, dev, timed, barrier):
         import gc
         steps = 10
         lib.epb_profile_enable(1)             # (kernel times of the same passes: two CUDA events per library call)
-        gc.collect(); gc.disable()
+        gc.disable()
         each = []
         for i in range(steps):
             barrier()
@@ -503,8 +503,7 @@ def run_ours(a):
         # short region has no queued work to hide that behind)
         import gc
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gc.collect()
-        gc.disable()
+        gc.disable()                          # (no gc.collect() here: tens of ms of idle GPU right before a short region)
         barrier()
         ev0.record()
         for _ in range(steps):
@@ -658,7 +657,7 @@ def run_ours(a):
                     "peak_source": "cudaMemcpyAsync of one rank's h2d bytes from pinned memory, all ranks at once, "
                                    "this run (rank 0's figure)"}},
         "gpu_launches": int(launches),
-        "host_gc": "Python's cyclic GC is disabled inside every timed region (timeit's convention) and collected before it",
+        "host_gc": "Python's cyclic GC is disabled inside every timed region (timeit's convention)",
 
         "roofline": {"kernel": "vote_count_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,

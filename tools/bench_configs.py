@@ -36,7 +36,6 @@ def timed(fn, steps, warmup=3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gc.collect()
     gc.disable()          # like timeit: a generation-2 collection stalls the enqueueing thread for tens of ms
     try:
         e0.record()

@@ -327,11 +327,13 @@ def secondary_configs(a, world, rank, dev, timed, barrier):
         for _ in range(5):
             full()
         torch.cuda.synchronize()
-        # Every pass is timed on its own (events between the passes, a barrier before each when there are several
-        # ranks; max over ranks per pass) and the MEDIAN pass is the figure: this leg is ~40 short launches per 3.3 ms
-        # pass, so the enqueueing thread is never far ahead of the GPU, and about one pass in fifty of a bench.py
-        # process picks up a 50-90 ms stall of that thread (not the garbage collector: it is off here; not seen in
-        # 900 passes of the same call in a process of its own).  The mean and every pass are reported next to it.
+        # Every pass is timed on its own (a barrier and a synchronisation per pass; max over ranks per pass) and the
+        # MEDIAN pass is the figure.  This leg is ~40 short launches plus a dozen event records / waits per 3.3 ms
+        # pass; timed as N back-to-back passes without a synchronisation, the enqueueing thread runs ahead until a
+        # launch queue is full, and the driver then parks it for 50-100 ms (the effect poses_from_vertex throttles
+        # against with its DEPTH ring): about one pass in fifty, enough to turn a 5-pass mean into 140-370 k poses/s
+        # in three of twenty runs.  A caller that consumes each call's result -- the per-pass synchronisation here --
+        # never gets there.  The mean and every pass are reported next to the median.
         import gc
         steps = 10
         lib.epb_profile_enable(1)             # (kernel times of the same passes: two CUDA events per library call)

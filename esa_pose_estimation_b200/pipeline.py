@@ -32,9 +32,15 @@ def poses_from_heatmaps(hms, bbox_xy, rate, p3d_model, K, min_k=24, sel_thresh=0
         return out
     dev = hms.device
     cur = torch.cuda.current_stream(dev)
-    ps = _pose_streams.get((dev.index, cur.cuda_stream))
-    if ps is None:
-        ps = _pose_streams[(dev.index, cur.cuda_stream)] = torch.cuda.Stream(device=dev, priority=-1)
+    st = _pose_streams.get((dev.index, cur.cuda_stream))
+    if st is None:
+        st = _pose_streams[(dev.index, cur.cuda_stream)] = {
+            "ps": torch.cuda.Stream(device=dev, priority=-1), "done": [None, None], "turn": 0}
+    ps = st["ps"]
+    # at most two chunked calls in flight per caller stream: a caller that never consumes its results would otherwise
+    # run ahead until a launch queue is full, and the driver then parks the thread for 50-100 ms (see _HostPipe)
+    if st["done"][st["turn"]] is not None:
+        st["done"][st["turn"]].synchronize()
     ready = torch.cuda.Event()
     ready.record(cur)                        # bbox / rate / model / K of the caller's stream
     ps.wait_event(ready)
@@ -56,6 +62,8 @@ def poses_from_heatmaps(hms, bbox_xy, rate, p3d_model, K, min_k=24, sel_thresh=0
         done = torch.cuda.Event()
         done.record(ps)
     cur.wait_event(done)
+    st["done"][st["turn"]] = done
+    st["turn"] ^= 1
     for t in out.values():
         t.record_stream(cur)
     return out
